@@ -1,0 +1,146 @@
+/* skfem_b200.h -- C ABI of the B200-native finite element assembly engine.
+ *
+ * Drop-in boundary for the scikit-fem (v12.0.1) assembly hot path
+ *     CellBasis(mesh, elem) -> BilinearForm/LinearForm._assemble -> COOData -> CSR
+ * The reference is pure Python and has no FFI; the seams these entry points
+ * replace are the Python call signatures listed in SURVEY.md section 8(b).
+ * Each entry point names the reference code (paths relative to
+ * /root/reference/skfem/) whose arithmetic it reproduces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns and allocates every buffer (inputs, outputs, scratch);
+ *     nothing is retained between calls, the library holds no global state;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *     calls return without synchronising unless documented otherwise;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative
+ *     SKB_E* code for argument errors.  Nothing throws.
+ *   - arithmetic is IEEE-754 binary64, round-to-nearest, NO fused
+ *     multiply-add contraction, in the reference's operation order
+ *     (SURVEY.md Appendix A), so element-local data is bit-identical to
+ *     numpy's and the value-dependent CSR pattern matches scipy's.
+ */
+#ifndef SKFEM_B200_H
+#define SKFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKB_OK 0
+#define SKB_EINVAL (-1)      /* bad argument / unsupported combination   */
+#define SKB_ETOOBIG (-2)     /* tables do not fit on-chip / index overflow */
+#define SKB_EZERODET (-3)    /* "Zero Jacobian determinant"               */
+
+/* mapping kinds */
+#define SKB_MAP_AFFINE 0     /* mapping/mapping_affine.py (tri, tet)      */
+#define SKB_MAP_ISO_HEX1 1   /* mapping/mapping_isoparametric.py on MeshHex1 */
+
+/* library bilinear forms (models/poisson.py:7-19, models/elasticity.py:35-53) */
+#define SKB_FORM_LAPLACE 0          /* dot(grad(u), grad(v))              */
+#define SKB_FORM_MASS 1             /* u * v   (vector: dot(u, v))        */
+#define SKB_FORM_VECTOR_LAPLACE 2   /* ddot(grad(u), grad(v))             */
+#define SKB_FORM_ELASTICITY 3       /* ddot(C(sym_grad(u)), sym_grad(v)); params = {Lambda, 2.*Mu} */
+/* library linear forms (models/poisson.py:22-24) */
+#define SKB_LFORM_UNIT_LOAD 0       /* v */
+
+/* A finite element space on a mesh: Mesh.p/.t (mesh/mesh.py:27-28,558-559),
+ * the reference tables of Element.lbasis at the quadrature points
+ * (element/element_h1.py:10-24) and the rule itself (quadrature.py:12-77). */
+typedef struct skb_space {
+  int32_t dim;        /* 2 | 3                                              */
+  int32_t nnodes;     /* rows of t: 3 (tri), 4 (tet), 8 (hex)               */
+  int32_t mapping;    /* SKB_MAP_*                                          */
+  int32_t nbs;        /* scalar basis functions per element                 */
+  int32_t ncomp;      /* 1, or dim for ElementVector (element_vector.py:36-48): local index = ncomp*b + n */
+  int32_t nqp;        /* quadrature points per element                      */
+  int64_t npts;       /* p.shape[1] (leading dimension of p)                */
+  int64_t nel_total;  /* t.shape[1]                                         */
+  const double *p;    /* (dim, npts)  float64, coordinate-major             */
+  const int32_t *t;   /* (nnodes, nel_total) int32, node-major              */
+  const int32_t *tind;/* optional element subset (CellBasis(elements=...)), NULL = all */
+  int64_t nel;        /* elements to process (= nel_total when tind==NULL)  */
+  const double *phi;  /* (nbs, nqp)        lbasis values                    */
+  const double *dphi; /* (nbs, dim, nqp)   lbasis reference gradients       */
+  const double *W;    /* (nqp,)            quadrature weights               */
+  const double *mdphi;/* (nnodes, dim, nqp) mapping-element gradients, ISO only */
+  const double *mphi; /* (nnodes, nqp)      mapping-element values, ISO only (global coords) */
+  const double *X;    /* (dim, nqp) quadrature points, needed by skb_global_coords (affine) */
+} skb_space_t;
+
+/* ---- element-local data: replaces CellBasis.__init__ + Form._assemble ----
+ * (assembly/basis/cell_basis.py:94-106; assembly/form/bilinear_form.py:58-128,
+ *  150-151; linear_form.py:18-49).  Geometry (mapping_affine.py:55-131 /
+ * mapping_isoparametric.py:112-226), push-forward (element_h1.py:17), the
+ * integrand and the numpy-pairwise quadrature sum are fused; nothing of shape
+ * (.., nel, nqp) is materialised.
+ * out_local: (Nbu, Nbv, nel) float64, C order == COOData.data before
+ * flatten (bilinear_form.py:121); Nbu = Nbv = nbs*ncomp.                   */
+int skb_local_bilinear(const skb_space_t *space, int form, const double *params_host,
+                       double *out_local, void *stream);
+/* out_local: (Nbv, nel) float64 (linear_form.py:41-44).                    */
+int skb_local_linear(const skb_space_t *space, int form, const double *params_host,
+                     double *out_local, void *stream);
+
+/* ---- sparsity plan: replaces COOData._assemble_scipy_csr's structure ----
+ * (assembly/form/coo_data.py:27-36 -> scipy coo_matrix.eliminate_zeros +
+ * tocsr: coo_tocsr, csr_sort_indices, csr_sum_duplicates).
+ * COO entry k = (j*Nbv + i)*nel + e has row = dofs_v[i*nel+e],
+ * col = dofs_u[j*nel+e] (bilinear_form.py:88-91).  Entries whose local value
+ * is == 0.0 are dropped when drop_zeros != 0 (coo_data.py:35), which makes the
+ * pattern value dependent.
+ *
+ * Step 1 (symbolic): stable device radix sort of (row*Ncols+col) keys, head
+ * flags and their scan.  Scratch is caller-provided:
+ *   keys_a/keys_b  uint64[ncoo], vals_a/vals_b uint32[ncoo], slot uint32[ncoo],
+ *   tmp: skb_plan_scratch_bytes(ncoo) bytes.
+ * Writes counts_host[0] = nnz (CSR slots), counts_host[1] = nkeep (surviving
+ * triplets), counts_host[2] = 0|1 (sorted keys/vals ended up in the *_a | *_b
+ * buffers) after synchronising the stream.  counts_host: int64[3].
+ * Step 2 (finalize): fills caller-allocated indptr int32[nrows+1],
+ * indices int32[nnz], segptr uint32[nnz+1], perm uint32[nkeep] where
+ * perm[segptr[s] .. segptr[s+1]) are the COO entries of slot s in stable COO
+ * order (entry-major, element-minor).                                       */
+int64_t skb_plan_scratch_bytes(int64_t ncoo);
+int skb_plan_symbolic(const int32_t *dofs_v, const int32_t *dofs_u, int32_t nbv, int32_t nbu,
+                      int64_t nel, int64_t nrows, int64_t ncols,
+                      const double *local_or_null, int drop_zeros,
+                      uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b,
+                      uint32_t *slot, void *tmp, int64_t tmp_bytes,
+                      int64_t *counts_host, void *stream);
+int skb_plan_finalize(int64_t ncoo, int64_t nrows, int64_t ncols, int64_t nnz, int64_t nkeep,
+                      const uint64_t *keys_sorted, const uint32_t *vals_sorted, const uint32_t *slot,
+                      int32_t *indptr, int32_t *indices, uint32_t *segptr, uint32_t *perm,
+                      void *stream);
+
+/* ---- numeric phase: replaces csr_sum_duplicates (coo_data.py:36) ----
+ * data[s] = sum of local[perm[k]], k in [segptr[s], segptr[s+1]), added
+ * sequentially in that fixed order: deterministic, no float atomics.       */
+int skb_csr_reduce(const double *local, const uint32_t *perm, const uint32_t *segptr,
+                   int64_t nnz, double *data, void *stream);
+/* LinearForm scatter, replaces COOData.toarray 1-tensor branch / scipy
+ * coo_todense (coo_data.py:102-108): vec[r] = sequential sum in COO order. */
+int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *segptr,
+                   const int32_t *indptr, int64_t nrows, double *vec, void *stream);
+
+/* ---- materialised basis for traced (user-defined) forms -----------------
+ * grad: (dim, nel, nqp) of scalar basis function b (element_h1.py:17);
+ * dx: (nel, nqp) (cell_basis.py:104-105); x: (dim, nel, nqp)
+ * (mapping_affine.py:183-193 / mapping_isoparametric.py:52-58,170-171);
+ * detabs: (nel, nqp) |detDF|.  Any output pointer may be NULL.             */
+int skb_tabulate(const skb_space_t *space, int b, double *grad, double *dx, double *x,
+                 double *detabs, void *stream);
+/* out[e] = numpy-pairwise sum over q of integrand[e,q]*dx[e,q]
+ * (bilinear_form.py:150-151; numpy pairwise_sum).                           */
+int skb_qp_reduce(const double *integrand, const double *dx, int64_t nel, int32_t nqp,
+                  double *out, void *stream);
+
+/* library / build identification */
+const char *skb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKFEM_B200_H */

@@ -1,0 +1,85 @@
+"""ctypes binding of the C-ABI library (include/skfem_b200.h).
+
+The shared object is built in-tree by ``__graft_entry__.build()`` (nvcc,
+sm_100a).  There is NO fallback: if it is missing, importing the compute path
+fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libskfem_b200.so")
+
+SKB_MAP_AFFINE, SKB_MAP_ISO_HEX1 = 0, 1
+FORM_LAPLACE, FORM_MASS, FORM_VECTOR_LAPLACE, FORM_ELASTICITY = 0, 1, 2, 3
+LFORM_UNIT_LOAD = 0
+
+ERRORS = {-1: "SKB_EINVAL: bad argument / unsupported combination",
+          -2: "SKB_ETOOBIG: tables do not fit on-chip or index overflow",
+          -3: "Zero Jacobian determinant"}
+
+
+class SkbSpace(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("nnodes", C.c_int32), ("mapping", C.c_int32),
+                ("nbs", C.c_int32), ("ncomp", C.c_int32), ("nqp", C.c_int32),
+                ("npts", C.c_int64), ("nel_total", C.c_int64),
+                ("p", C.c_void_p), ("t", C.c_void_p), ("tind", C.c_void_p),
+                ("nel", C.c_int64),
+                ("phi", C.c_void_p), ("dphi", C.c_void_p), ("W", C.c_void_p),
+                ("mdphi", C.c_void_p), ("mphi", C.c_void_p), ("X", C.c_void_p)]
+
+
+_P, _I64, _I32, _INT = C.c_void_p, C.c_int64, C.c_int32, C.c_int
+_SP = C.POINTER(SkbSpace)
+_PD = C.POINTER(C.c_double)
+
+SIGNATURES = {
+    "skb_local_bilinear": (_INT, [_SP, _INT, _PD, _P, _P]),
+    "skb_local_linear": (_INT, [_SP, _INT, _PD, _P, _P]),
+    "skb_plan_scratch_bytes": (_I64, [_I64]),
+    "skb_plan_symbolic": (_INT, [_P, _P, _I32, _I32, _I64, _I64, _I64, _P, _INT,
+                                 _P, _P, _P, _P, _P, _P, _I64, C.POINTER(_I64), _P]),
+    "skb_plan_finalize": (_INT, [_I64, _I64, _I64, _I64, _I64, _P, _P, _P,
+                                 _P, _P, _P, _P, _P]),
+    "skb_csr_reduce": (_INT, [_P, _P, _P, _I64, _P, _P]),
+    "skb_vec_reduce": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
+    "skb_tabulate": (_INT, [_SP, _INT, _P, _P, _P, _P, _P]),
+    "skb_qp_reduce": (_INT, [_P, _P, _I64, _I32, _P, _P]),
+    "skb_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+def lib():
+    """Load (once) and return the native library; raise if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                "skfem_b200: native library {} not found. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` - there is "
+                "no CPU fallback.".format(LIB_PATH))
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code, what=""):
+    if code == 0:
+        return
+    if code == -3:
+        raise Exception("Zero Jacobian determinant")
+    if code < 0:
+        raise ValueError("{}: {}".format(what, ERRORS.get(code, code)))
+    raise RuntimeError("{}: CUDA error {}".format(what, code))

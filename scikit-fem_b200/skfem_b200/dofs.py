@@ -1,0 +1,65 @@
+"""Global degree-of-freedom numbering.
+
+Bit-exact restatement of the layout produced by the reference's
+``Dofs.__init__`` (skfem/assembly/dofs.py:264-334): vertex DOFs first
+(``nd*vertex + component``), then edge, facet and interior blocks; the
+``element_dofs`` rows follow local vertices, local edges (``t2e`` rows), local
+facets (``t2f`` rows), interior.  Everything is int32.
+
+Host side: the numbering is built once per (mesh, element) from the mesh
+topology and uploaded; the kernels only ever read ``element_dofs``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _block(ndofs_per_entity, nentities, offset):
+    """(ndofs, nentities) table numbered entity-major, starting at offset."""
+    tab = np.arange(ndofs_per_entity * nentities, dtype=np.int32)
+    return tab.reshape((ndofs_per_entity, nentities), order='F') + np.int32(offset)
+
+
+class Dofs:
+
+    def __init__(self, topo, element, offset=0):
+        self.topo = topo
+        self.element = element
+        nel = topo.nelements
+        three_d = element.dim == 3
+
+        self.nodal_dofs = _block(element.nodal_dofs, topo.nvertices, offset)
+        offset += self.nodal_dofs.size
+
+        if three_d and element.edge_dofs > 0:
+            self.edge_dofs = _block(element.edge_dofs, topo.nedges, offset)
+            offset += self.edge_dofs.size
+        else:
+            self.edge_dofs = np.empty((0, 0), dtype=np.int32)
+
+        if element.facet_dofs > 0:
+            self.facet_dofs = _block(element.facet_dofs, topo.nfacets, offset)
+            offset += self.facet_dofs.size
+        else:
+            self.facet_dofs = np.empty((0, 0), dtype=np.int32)
+
+        self.interior_dofs = _block(element.interior_dofs, nel, offset)
+
+        parts = [self.nodal_dofs[:, topo.t[k]] for k in range(topo.t.shape[0])]
+        if self.edge_dofs.size:
+            parts += [self.edge_dofs[:, topo.t2e[k]] for k in range(topo.t2e.shape[0])]
+        if element.dim >= 2 and self.facet_dofs.size:
+            parts += [self.facet_dofs[:, topo.t2f[k]] for k in range(topo.t2f.shape[0])]
+        parts.append(self.interior_dofs)
+        self.element_dofs = np.ascontiguousarray(np.vstack(parts), dtype=np.int32)
+        self.N = int(np.max(self.element_dofs)) + 1
+
+    def boundary(self):
+        """All DOFs attached to boundary vertices / edges / facets."""
+        m = self.topo
+        out = [self.nodal_dofs[:, m.boundary_nodes()].flatten()]
+        if self.edge_dofs.size:
+            out.append(self.edge_dofs[:, m.boundary_edges()].flatten())
+        if self.facet_dofs.size:
+            out.append(self.facet_dofs[:, m.boundary_facets()].flatten())
+        return np.unique(np.concatenate(out)).astype(np.int32)

@@ -1,0 +1,497 @@
+"""Forms and their assembly: ``BilinearForm``, ``LinearForm``, ``Functional``,
+``COOData``, ``asm`` - the reference's ``skfem.assembly.form`` surface
+(skfem/assembly/form/form.py:28-121, bilinear_form.py:17-161,
+linear_form.py:10-49, functional.py:11-61, coo_data.py:19-242,
+skfem/assembly/__init__.py:63-97) on top of the CUDA engine.
+
+Pipeline of ``form.assemble(basis)``:
+
+1. element-local data ``(Nbu, Nbv, nel)`` on the device
+   - library forms (``skfem_b200.models``): one fused kernel
+     (``skb_local_bilinear`` / ``skb_local_linear``),
+   - user forms: *traced* - the Python callable runs once per local entry on
+     device fields, the quadrature reduction is ``skb_qp_reduce``;
+2. sparsity plan (cached per basis/form): ``skb_plan_symbolic`` +
+   ``skb_plan_finalize`` - value-dependent pattern like scipy's
+   ``eliminate_zeros().tocsr()``;
+3. numeric phase ``skb_csr_reduce`` / ``skb_vec_reduce`` - deterministic
+   segmented sums;
+4. the result is handed back as ``scipy.sparse.csr_matrix`` / ``ndarray`` or,
+   with ``assemble_device``, kept on the GPU as :class:`DeviceCSR`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import numbers
+import warnings
+from copy import deepcopy
+from dataclasses import dataclass, replace
+from functools import partial
+from inspect import signature
+from typing import Any, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .field import DeviceArray, DiscreteField
+
+logger = logging.getLogger(__name__)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class FormExtraParams(dict):
+    """Passed to forms as 'w'."""
+
+    def __getattr__(self, attr):
+        if attr in self:
+            return self[attr]
+        raise AttributeError("Attribute '{}' not found in 'w'.".format(attr))
+
+
+# ---------------------------------------------------------------------------
+# device CSR + sparsity plan
+# ---------------------------------------------------------------------------
+class DeviceCSR:
+    """CSR matrix resident on the GPU: ``indptr``/``indices`` int32, ``data``
+    float64 torch tensors (canonical format: sorted, no duplicates)."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr, self.indices, self.data, self.shape = indptr, indices, data, tuple(shape)
+
+    @property
+    def nnz(self):
+        return int(self.data.shape[0])
+
+    def to_scipy(self):
+        from scipy.sparse import csr_matrix
+        A = csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
+                        self.indptr.cpu().numpy()), shape=self.shape)
+        A.has_sorted_indices = True
+        A.has_canonical_format = True
+        return A
+
+    tocsr = to_scipy
+
+    def to_torch(self):
+        torch = _torch()
+        return torch.sparse_csr_tensor(self.indptr.long(), self.indices.long(), self.data,
+                                       size=self.shape)
+
+    def matvec(self, x):
+        return self.to_torch() @ x
+
+
+class Plan:
+    """indptr/indices + the entry->slot permutation of one (basis, form)."""
+    __slots__ = ("indptr", "indices", "segptr", "perm", "nnz", "nkeep", "shape", "ncoo")
+
+
+def _stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def build_plan(dofs_v, dofs_u, nel, shape, local, drop_zeros=True):
+    """Sort/unique on the device (skb_plan_symbolic + skb_plan_finalize)."""
+    torch = _torch()
+    lib = _lib.lib()
+    dev = dofs_v.device
+    nbv = dofs_v.shape[0]
+    nbu = 1 if dofs_u is None else dofs_u.shape[0]
+    ncoo = nbv * nbu * nel
+    nrows = int(shape[0])
+    ncols = int(shape[1]) if len(shape) > 1 else 1
+    plan = Plan()
+    plan.shape, plan.ncoo = tuple(shape), ncoo
+    i32, i64 = torch.int32, torch.int64
+    if ncoo == 0:
+        plan.nnz = plan.nkeep = 0
+        plan.indptr = torch.zeros(nrows + 1, dtype=i32, device=dev)
+        plan.indices = torch.zeros(0, dtype=i32, device=dev)
+        plan.segptr = torch.zeros(1, dtype=i32, device=dev)
+        plan.perm = torch.zeros(0, dtype=i32, device=dev)
+        return plan
+    keys_a = torch.empty(ncoo, dtype=i64, device=dev)
+    keys_b = torch.empty(ncoo, dtype=i64, device=dev)
+    vals_a = torch.empty(ncoo, dtype=i32, device=dev)
+    vals_b = torch.empty(ncoo, dtype=i32, device=dev)
+    slot = torch.empty(ncoo, dtype=i32, device=dev)
+    tmp_bytes = int(lib.skb_plan_scratch_bytes(ncoo))
+    tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=dev)
+    counts = (C.c_int64 * 3)()
+    code = lib.skb_plan_symbolic(
+        dofs_v.data_ptr(), None if dofs_u is None else dofs_u.data_ptr(), nbv, nbu, nel,
+        nrows, ncols, None if local is None else local.data_ptr(), 1 if drop_zeros else 0,
+        keys_a.data_ptr(), keys_b.data_ptr(), vals_a.data_ptr(), vals_b.data_ptr(),
+        slot.data_ptr(), tmp.data_ptr(), tmp_bytes, counts, _stream())
+    _lib.check(code, "skb_plan_symbolic")
+    nnz, nkeep, which = int(counts[0]), int(counts[1]), int(counts[2])
+    ks, vs = (keys_a, vals_a) if which == 0 else (keys_b, vals_b)
+    plan.nnz, plan.nkeep = nnz, nkeep
+    plan.indptr = torch.empty(nrows + 1, dtype=i32, device=dev)
+    plan.indices = torch.empty(nnz, dtype=i32, device=dev)
+    plan.segptr = torch.empty(nnz + 1, dtype=i32, device=dev)
+    plan.perm = torch.empty(max(nkeep, 1), dtype=i32, device=dev)
+    code = lib.skb_plan_finalize(ncoo, nrows, ncols, nnz, nkeep, ks.data_ptr(), vs.data_ptr(),
+                                 slot.data_ptr(), plan.indptr.data_ptr(),
+                                 plan.indices.data_ptr(), plan.segptr.data_ptr(),
+                                 plan.perm.data_ptr(), _stream())
+    _lib.check(code, "skb_plan_finalize")
+    return plan
+
+
+# ---------------------------------------------------------------------------
+# COOData
+# ---------------------------------------------------------------------------
+@dataclass
+class COOData:
+    """Element-local (COO) form of an assembled tensor, host numpy arrays with
+    the reference's layout (coo_data.py:19-25): ``data`` flattened
+    entry-major / element-minor, ``indices`` int32 ``[rows, cols]``."""
+    indices: np.ndarray
+    data: np.ndarray
+    shape: Tuple[int, ...]
+    local_shape: Optional[Tuple[int, ...]]
+
+    def tolocal(self, basis=None):
+        if self.local_shape is None:
+            raise NotImplementedError("Cannot build local matrices if "
+                                      "local_shape is not specified.")
+        return np.moveaxis(self.data.reshape(self.local_shape + (-1,), order='C'), -1, 0)
+
+    def fromlocal(self, local):
+        return replace(self, data=np.moveaxis(local, 0, -1).flatten('C'))
+
+    def __add__(self, other):
+        if isinstance(other, int):
+            return self
+        return replace(self, indices=np.hstack((self.indices, other.indices)),
+                       data=np.hstack((self.data, other.data)),
+                       shape=tuple(max(a, b) for a, b in zip(self.shape, other.shape)),
+                       local_shape=None)
+
+    __radd__ = __add__
+
+    def astuple(self):
+        return self.indices, self.data, self.shape
+
+    def _device_reduce(self):
+        """Assemble arbitrary (possibly concatenated) COO triplets on the GPU."""
+        torch = _torch()
+        from .basis import default_device
+        dev = default_device()
+        data = torch.as_tensor(self.data, dtype=torch.float64, device=dev)
+        rows = torch.as_tensor(self.indices[0].astype(np.int32), device=dev).reshape(1, -1)
+        n = rows.shape[1]
+        if len(self.shape) == 2:
+            cols = torch.as_tensor(self.indices[1].astype(np.int32), device=dev).reshape(1, -1)
+            plan = build_plan(rows, cols, n, self.shape, data, drop_zeros=True)
+            out = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+            _lib.check(_lib.lib().skb_csr_reduce(data.data_ptr(), plan.perm.data_ptr(),
+                                                 plan.segptr.data_ptr(), plan.nnz,
+                                                 out.data_ptr(), _stream()), "skb_csr_reduce")
+            return DeviceCSR(plan.indptr, plan.indices, out, self.shape)
+        plan = build_plan(rows, None, n, self.shape, None, drop_zeros=False)
+        out = torch.empty(self.shape[0], dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().skb_vec_reduce(data.data_ptr(), plan.perm.data_ptr(),
+                                             plan.segptr.data_ptr(), plan.indptr.data_ptr(),
+                                             self.shape[0], out.data_ptr(), _stream()),
+                   "skb_vec_reduce")
+        return out
+
+    def tocsr(self):
+        return self._device_reduce().to_scipy()
+
+    def toarray(self):
+        if len(self.shape) == 1:
+            return self._device_reduce().cpu().numpy()
+        if len(self.shape) == 2:
+            return self.tocsr().toarray()
+        raise NotImplementedError
+
+    def todefault(self):
+        if len(self.shape) == 0:
+            return np.sum(self.data, axis=0)
+        if len(self.shape) == 1:
+            return self.toarray()
+        if len(self.shape) == 2:
+            return self.tocsr()
+        return self
+
+
+# ---------------------------------------------------------------------------
+# forms
+# ---------------------------------------------------------------------------
+class Form:
+    form = None
+    native = None  # ("bilinear"|"linear", kernel id, params, "scalar"|"vector")
+
+    def __init__(self, form=None, dtype=np.float64, nthreads=0, **params):
+        self.form = form.form if isinstance(form, Form) else form
+        if isinstance(form, Form):
+            self.native = form.native
+        self.nargs = len(signature(self.form).parameters) if self.form is not None else None
+        if dtype not in (np.float64, float):
+            raise NotImplementedError("skfem_b200 assembles in float64 only")
+        self.dtype = dtype
+        self.nthreads = nthreads  # accepted for API compatibility; the GPU path ignores it
+        self.params = params
+
+    def partial(self, *args, **kwargs):
+        form = deepcopy(self)
+        name = form.form.__name__
+        form.form = partial(form.form, *args, **kwargs)
+        form.form.__name__ = name
+        form.native = None
+        return form
+
+    def __call__(self, *args):
+        if self.form is None:  # used as a decorator factory
+            return type(self)(form=args[0], dtype=self.dtype, nthreads=self.nthreads,
+                              **self.params)
+        return self.form(*args)
+
+    # -- shared machinery -------------------------------------------------------------
+    @staticmethod
+    def _normalize_asm_kwargs(w, basis):
+        """Accepted formats of the extra parameters (form.py:91-121)."""
+        torch = _torch()
+        out = {}
+        for k, v in w.items():
+            if isinstance(v, DiscreteField):
+                if v.shape[-1] != basis.X.shape[-1]:
+                    raise ValueError("Quadrature mismatch: '{}' should have same number of "
+                                     "integration points as the basis object.".format(k))
+                out[k] = v
+            elif isinstance(v, DeviceArray):
+                out[k] = DiscreteField(v.t)
+            elif isinstance(v, numbers.Number) or isinstance(v, tuple):
+                out[k] = v
+            elif torch.is_tensor(v):
+                out[k] = basis.interpolate(v) if v.dim() == 1 else DiscreteField(v)
+            elif isinstance(v, np.ndarray) and v.ndim == 1:
+                out[k] = basis.interpolate(v)
+            elif isinstance(v, np.ndarray) and v.ndim > 1:
+                dev = basis._dev()["device"]
+                out[k] = DiscreteField(torch.as_tensor(np.asarray(v, dtype=np.float64), device=dev))
+            elif isinstance(v, list):
+                warnings.warn("Use Basis.interpolate instead of passing lists to assemble",
+                              DeprecationWarning)
+                out[k] = v
+            else:
+                raise ValueError("The given type '{}' for the list of extra form parameters w "
+                                 "cannot be converted to DiscreteField.".format(type(v)))
+        return out
+
+    def _wdict(self, basis, kwargs):
+        return FormExtraParams({**basis.default_parameters(),
+                                **self._normalize_asm_kwargs(kwargs, basis)})
+
+    def _reduce_qp(self, basis, integrand, out_row):
+        """out_row[e] = numpy-pairwise sum_q integrand[e, q] * dx[e, q]."""
+        torch = _torch()
+        nel, nqp = basis.nelems, basis.nqp
+        t = integrand.t if isinstance(integrand, DeviceArray) else integrand
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(t, dtype=torch.float64, device=out_row.device)
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        t = t.expand(nel, nqp).contiguous()
+        code = _lib.lib().skb_qp_reduce(t.data_ptr(), basis._dx_dev().data_ptr(), nel, nqp,
+                                        out_row.data_ptr(), _stream())
+        _lib.check(code, "skb_qp_reduce")
+
+    def assemble(self, *args, **kwargs) -> Any:
+        raise NotImplementedError
+
+    def elemental(self, *args, **kwargs):
+        return self.coo_data(*args, **kwargs)
+
+
+class BilinearForm(Form):
+    """``a(u, v)``: ``form(u, v, w)`` integrated over the basis.
+
+    >>> form = BilinearForm(lambda u, v, _: u * v)
+    >>> form.assemble(Basis(MeshTri(), ElementTriP1())).toarray()  # 4x4 mass matrix
+    """
+
+    def _native_applicable(self, ubasis, vbasis, kwargs):
+        if self.native is None or kwargs or (vbasis is not None and vbasis is not ubasis):
+            return False
+        kind, _, _, field = self.native
+        if kind != "bilinear":
+            return False
+        if field == "scalar":
+            return ubasis.ncomp == 1
+        return ubasis.ncomp > 1
+
+    def _local(self, ubasis, vbasis=None, **kwargs):
+        """Element-local data (Nbu, Nbv, nel) as a device tensor."""
+        torch = _torch()
+        if vbasis is None:
+            vbasis = ubasis
+        elif ubasis.X.shape[-1] != vbasis.X.shape[-1]:
+            raise ValueError("Quadrature mismatch: trial and test functions "
+                             "should have same number of integration points.")
+        d = ubasis._dev()
+        nel = ubasis.nelems
+        out = torch.empty((ubasis.Nbfun, vbasis.Nbfun, nel), dtype=torch.float64,
+                          device=d["device"])
+        if self._native_applicable(ubasis, vbasis if vbasis is not ubasis else None, kwargs):
+            _, kid, params, _ = self.native
+            cparams = None if params is None else (C.c_double * len(params))(*params)
+            code = _lib.lib().skb_local_bilinear(C.byref(d["space"]), kid, cparams,
+                                                 out.data_ptr(), _stream())
+            _lib.check(code, "skb_local_bilinear")
+            return out
+        # traced path (bilinear_form.py:86-98 with device fields)
+        w = self._wdict(ubasis, kwargs)
+        ub = [ubasis._basis_field_dev(j) for j in range(ubasis.Nbfun)]
+        vb = ub if vbasis is ubasis else [vbasis._basis_field_dev(i) for i in range(vbasis.Nbfun)]
+        for j in range(ubasis.Nbfun):
+            for i in range(vbasis.Nbfun):
+                self._reduce_qp(ubasis, self.form(ub[j], vb[i], w), out[j, i])
+        return out
+
+    def _plan_key(self, ubasis, vbasis, kwargs):
+        if kwargs:
+            return None
+        return (id(self.form) if self.native is None else self.native[:3],
+                id(vbasis) if vbasis is not None else None)
+
+    def assemble_device(self, ubasis, vbasis=None, **kwargs) -> DeviceCSR:
+        """Assemble into a device-resident CSR (no host transfer)."""
+        assert self.form is not None
+        torch = _torch()
+        vb = ubasis if vbasis is None else vbasis
+        local = self._local(ubasis, vbasis, **kwargs)
+        key = self._plan_key(ubasis, vbasis, kwargs)
+        plan = ubasis._plans.get(key) if key is not None else None
+        if plan is None:
+            plan = build_plan(vb._dev()["edofs"], ubasis._dev()["edofs"], ubasis.nelems,
+                              (vb.N, ubasis.N), local, drop_zeros=True)
+            if key is not None:
+                ubasis._plans[key] = plan
+        data = torch.empty(plan.nnz, dtype=torch.float64, device=local.device)
+        code = _lib.lib().skb_csr_reduce(local.data_ptr(), plan.perm.data_ptr(),
+                                         plan.segptr.data_ptr(), plan.nnz, data.data_ptr(),
+                                         _stream())
+        _lib.check(code, "skb_csr_reduce")
+        return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
+
+    def assemble(self, ubasis, vbasis=None, **kwargs):
+        """Assemble into ``scipy.sparse.csr_matrix`` (bilinear_form.py:130-148)."""
+        logger.info("Assembling '{}'.".format(getattr(self.form, "__name__", "form")))
+        A = self.assemble_device(ubasis, vbasis, **kwargs).to_scipy()
+        logger.info("Assembling finished.")
+        return A
+
+    def coo_data(self, ubasis, vbasis=None, **kwargs) -> COOData:
+        """Element-local matrices as host COO data (form.py:82-89)."""
+        vb = ubasis if vbasis is None else vbasis
+        local = self._local(ubasis, vbasis, **kwargs)
+        nel = ubasis.nelems
+        rows = np.tile(vb.element_dofs, (ubasis.Nbfun, 1)).reshape(-1)
+        cols = np.repeat(ubasis.element_dofs, vb.Nbfun, axis=0).reshape(-1)
+        assert rows.shape[0] == ubasis.Nbfun * vb.Nbfun * nel
+        return COOData(np.array([rows, cols]), local.reshape(-1).cpu().numpy(),
+                       (vb.N, ubasis.N), (vb.Nbfun, ubasis.Nbfun))
+
+    def _assemble(self, ubasis, vbasis=None, **kwargs):
+        c = self.coo_data(ubasis, vbasis, **kwargs)
+        return c.indices, c.data, c.shape, c.local_shape
+
+
+class LinearForm(Form):
+    """``l(v)``: ``form(v, w)`` integrated over the basis."""
+
+    def _local(self, basis, **kwargs):
+        torch = _torch()
+        d = basis._dev()
+        out = torch.empty((basis.Nbfun, basis.nelems), dtype=torch.float64, device=d["device"])
+        if (self.native is not None and not kwargs and self.native[0] == "linear"
+                and basis.ncomp == 1):
+            code = _lib.lib().skb_local_linear(C.byref(d["space"]), self.native[1], None,
+                                               out.data_ptr(), _stream())
+            _lib.check(code, "skb_local_linear")
+            return out
+        w = self._wdict(basis, kwargs)
+        for i in range(basis.Nbfun):
+            self._reduce_qp(basis, self.form(basis._basis_field_dev(i), w), out[i])
+        return out
+
+    def assemble_device(self, basis, vbasis=None, **kwargs):
+        assert vbasis is None
+        assert self.form is not None
+        torch = _torch()
+        local = self._local(basis, **kwargs)
+        plan = basis._plans.get("linear")
+        if plan is None:
+            plan = build_plan(basis._dev()["edofs"], None, basis.nelems, (basis.N,), None,
+                              drop_zeros=False)
+            basis._plans["linear"] = plan
+        vec = torch.empty(basis.N, dtype=torch.float64, device=local.device)
+        code = _lib.lib().skb_vec_reduce(local.data_ptr(), plan.perm.data_ptr(),
+                                         plan.segptr.data_ptr(), plan.indptr.data_ptr(),
+                                         basis.N, vec.data_ptr(), _stream())
+        _lib.check(code, "skb_vec_reduce")
+        return vec
+
+    def assemble(self, basis, vbasis=None, **kwargs):
+        return self.assemble_device(basis, vbasis, **kwargs).cpu().numpy()
+
+    def coo_data(self, basis, vbasis=None, **kwargs) -> COOData:
+        assert vbasis is None
+        local = self._local(basis, **kwargs)
+        rows = basis.element_dofs.reshape(-1)
+        return COOData(np.array([rows]), local.reshape(-1).cpu().numpy(), (basis.N,),
+                       (basis.Nbfun,))
+
+    def _assemble(self, basis, vbasis=None, **kwargs):
+        c = self.coo_data(basis, vbasis, **kwargs)
+        return c.indices, c.data, c.shape, c.local_shape
+
+
+class Functional(Form):
+    """Scalar functional ``form(w)`` integrated over the basis
+    (functional.py:11-61)."""
+
+    def elemental(self, basis, **kwargs):
+        torch = _torch()
+        if self.form is None:
+            raise Exception("Form function handle not defined.")
+        w = self._wdict(basis, kwargs)
+        out = torch.empty(basis.nelems, dtype=torch.float64, device=basis._dev()["device"])
+        self._reduce_qp(basis, self.form(w), out)
+        return out.cpu().numpy()
+
+    def assemble(self, basis, vbasis=None, **kwargs):
+        assert vbasis is None
+        return np.sum(self.elemental(basis, **kwargs), axis=0)
+
+    def coo_data(self, basis, vbasis=None, **kwargs):
+        return COOData(np.array([]), np.array([self.assemble(basis, **kwargs)]), (), ())
+
+
+def asm(form, *args, to=None, **kwargs):
+    """Shorthand for ``form.assemble`` (skfem/assembly/__init__.py:69-97).
+    Bare callables are wrapped by argument count.  Lists of bases are summed
+    through concatenated COO data, assembled once on the device."""
+    if not isinstance(form, Form) and callable(form):
+        nargs = form.__code__.co_argcount
+        form = [Functional, LinearForm, BilinearForm][nargs - 1](form)
+    assert form.form is not None
+    if any(isinstance(a, list) for a in args):
+        from itertools import product
+        lists = [a if isinstance(a, list) else [a] for a in args]
+        blocks = [form.coo_data(*combo, idx=ix, **kwargs)
+                  for ix, combo in zip(product(*(range(len(x)) for x in lists)), product(*lists))]
+        out = sum(blocks)
+        return out.todefault() if to is None else to(blocks)
+    if to is not None:
+        return to([form.coo_data(*args, **kwargs)])
+    return form.assemble(*args, **kwargs)

@@ -1,0 +1,321 @@
+"""Meshes: ``p`` (dim, nverts) float64 and ``t`` (nnodes, nel) int32 plus the
+lazily built topology needed for DOF numbering.
+
+Host side (numpy) by design: mesh generation is not the path being accelerated
+(SURVEY.md section 2 row 14).  Layout, dtypes and the vertex/element ordering of
+the constructors follow the reference so that ``p``/``t`` are bit-identical:
+
+* container + dtype normalisation        skfem/mesh/mesh.py:27-28,544-607
+* edges/facets = unique sorted tuples    skfem/mesh/mesh.py:1065-1082
+* MeshTet.init_tensor (6 Kuhn tets/cell) skfem/mesh/mesh_tet_1.py:326-393
+* MeshHex.init_tensor                    skfem/mesh/mesh_hex_1.py:97-155
+* MeshTri defaults / uniform refinement  skfem/mesh/mesh_tri_1.py:14-28,209-227
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .element import ElementTriP1, ElementTetP1, ElementHex1
+from .refdom import RefTri, RefTet, RefHex
+
+
+class Mesh:
+    elem = None          # geometry element (class)
+    affine = False
+    sort_t = False
+
+    def __init__(self, doflocs=None, t=None, validate=True, **_ignored):
+        if doflocs is None:
+            doflocs, t = self._default()
+        t = np.asarray(t)
+        if self.sort_t:
+            t = np.sort(t, axis=0)
+        self.doflocs = np.ascontiguousarray(np.asarray(doflocs, dtype=np.float64))
+        self.t = np.ascontiguousarray(t.astype(np.int32, copy=False))
+        if self.t.shape[0] != self.refdom.nnodes:
+            raise ValueError("t must have {} rows".format(self.refdom.nnodes))
+        if self.doflocs.shape[0] != self.refdom.dim():
+            raise ValueError("p must have {} rows".format(self.refdom.dim()))
+        self._dev = {}
+
+    # -- basic queries -------------------------------------------------------
+    @property
+    def p(self):
+        return self.doflocs
+
+    @property
+    def refdom(self):
+        return self.elem.refdom
+
+    def dim(self):
+        return self.refdom.dim()
+
+    @property
+    def nelements(self):
+        return self.t.shape[1]
+
+    @property
+    def nvertices(self):
+        return int(np.max(self.t)) + 1
+
+    @property
+    def nnodes(self):
+        return self.t.shape[0]
+
+    @property
+    def nfacets(self):
+        return self.facets.shape[1]
+
+    @property
+    def nedges(self):
+        if self.refdom.edges is None:
+            raise NotImplementedError
+        return self.edges.shape[1]
+
+    def __repr__(self):
+        return "<skfem_b200 {} object>\n  Number of elements: {}\n  Number of vertices: {}".format(
+            type(self).__name__, self.nelements, self.nvertices)
+
+    # -- topology --------------------------------------------------------------
+    @staticmethod
+    def build_entities(t, indices, sort=True):
+        """Lower-dimensional entities as the lexicographically sorted unique
+        columns of the per-element sorted vertex tuples, and the element ->
+        entity incidence."""
+        stacked = np.hstack([t[ix] for ix in indices])
+        canon = np.sort(stacked, axis=0)
+        canon, first, inverse = np.unique(canon, axis=1, return_index=True,
+                                          return_inverse=True)
+        incidence = inverse.reshape((len(indices), t.shape[1]))
+        if sort:
+            return np.ascontiguousarray(canon), incidence
+        return np.ascontiguousarray(stacked[:, first]), incidence
+
+    _sort_facets = True
+
+    def _init_facets(self):
+        self._facets, self._t2f = self.build_entities(self.t, self.refdom.facets,
+                                                      sort=self._sort_facets)
+
+    def _init_edges(self):
+        self._edges, self._t2e = self.build_entities(self.t, self.refdom.edges)
+
+    @property
+    def facets(self):
+        if not hasattr(self, "_facets"):
+            self._init_facets()
+        return self._facets
+
+    @property
+    def t2f(self):
+        if not hasattr(self, "_t2f"):
+            self._init_facets()
+        return self._t2f
+
+    @property
+    def edges(self):
+        if not hasattr(self, "_edges"):
+            self._init_edges()
+        return self._edges
+
+    @property
+    def t2e(self):
+        if not hasattr(self, "_t2e"):
+            self._init_edges()
+        return self._t2e
+
+    @property
+    def f2t(self):
+        """(2, nfacets): the one or two elements sharing each facet (-1)."""
+        if not hasattr(self, "_f2t"):
+            nf = self.nfacets
+            flat = self.t2f.flatten(order='C')
+            owner = np.tile(np.arange(self.nelements), self.t2f.shape[0])
+            out = np.full((2, nf), -1, dtype=np.int32)
+            order = np.argsort(flat, kind='stable')
+            fs, es = flat[order], owner[order]
+            start = np.r_[True, fs[1:] != fs[:-1]]
+            last = np.r_[fs[1:] != fs[:-1], True]
+            out[0, fs[start]] = es[start]
+            two = last & ~start
+            out[1, fs[two]] = es[two]
+            self._f2t = out
+        return self._f2t
+
+    def boundary_facets(self):
+        return np.nonzero(self.f2t[1] == -1)[0].astype(np.int32)
+
+    def boundary_nodes(self):
+        return np.unique(self.facets[:, self.boundary_facets()])
+
+    def boundary_edges(self):
+        """Edges (3-D) lying on boundary facets."""
+        bf = self.facets[:, self.boundary_facets()]
+        n = bf.shape[0]
+        pairs = np.hstack([np.sort(bf[[a, (a + 1) % n]], axis=0) for a in range(n)])
+        if self.refdom is RefTet:
+            cand = pairs
+        else:  # quads of a hex: consecutive vertices along the facet loop
+            cand = pairs
+        nv = self.nvertices
+        key = self.edges[0].astype(np.int64) * nv + self.edges[1]
+        ckey = np.unique(cand[0].astype(np.int64) * nv + cand[1])
+        return np.nonzero(np.isin(key, ckey))[0].astype(np.int32)
+
+    def normalize_elements(self, elements):
+        if isinstance(elements, (int, np.integer)):
+            return np.array([elements], dtype=np.int32)
+        arr = np.asarray(elements)
+        if arr.dtype == bool:
+            arr = np.nonzero(arr)[0]
+        return arr.astype(np.int32)
+
+    # -- geometry --------------------------------------------------------------
+    def _mapping(self):
+        from .mapping import MappingAffine, MappingIsoparametric
+        if not hasattr(self, "_cached_mapping"):
+            self._cached_mapping = (MappingAffine(self) if self.affine
+                                    else MappingIsoparametric(self, self.elem()))
+        return self._cached_mapping
+
+    def mapping(self):
+        return self._mapping()
+
+    def refined(self, times_or_ix=1):
+        m = self
+        for _ in range(int(times_or_ix)):
+            m = m._uniform()
+        return m
+
+    def _uniform(self):
+        raise NotImplementedError("uniform refinement is not implemented for "
+                                  + type(self).__name__)
+
+    def morphed(self, *args):
+        """Apply one function per coordinate (``None`` keeps it)."""
+        p = self.p.copy()
+        for i, f in enumerate(args):
+            if f is not None:
+                p[i] = f(self.p)
+        return type(self)(p, self.t)
+
+    def translated(self, diffs):
+        p = self.p.copy()
+        for i, d in enumerate(diffs):
+            p[i] += d
+        return type(self)(p, self.t)
+
+    def scaled(self, factors):
+        p = self.p.copy()
+        if np.isscalar(factors):
+            factors = self.p.shape[0] * (factors,)
+        for i, f in enumerate(factors):
+            p[i] *= f
+        return type(self)(p, self.t)
+
+    # -- device mirror -----------------------------------------------------------
+    def device_arrays(self, device):
+        """(p, t) as torch tensors on ``device``, uploaded once per mesh."""
+        import torch
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = (
+                torch.from_numpy(self.doflocs).to(device, non_blocking=False),
+                torch.from_numpy(self.t).to(device, non_blocking=False),
+            )
+        return self._dev[key]
+
+
+def _tensor_grid(x, y, z):
+    """Vertices of a tensor grid (vertex index = iy + npy*ix + npy*npx*iz) and
+    the eight corner rows of each cell, cells enumerated the same way."""
+    npx, npy, npz = len(x), len(y), len(z)
+    X, Y, Z = np.meshgrid(np.sort(x), np.sort(y), np.sort(z))
+    p = np.vstack((X.flatten('F'), Y.flatten('F'), Z.flatten('F')))
+    ix = np.arange(npx * npy * npz, dtype=np.int64).reshape(npy, npx, npz, order='F')
+    ne = (npx - 1) * (npy - 1) * (npz - 1)
+    cell = ix[:-1, :-1, :-1].reshape(ne, order='F')
+    sy, sx, sz = 1, npy, npy * npx
+    offs = [0, sy, sx, sz, sy + sx, sy + sz, sx + sz, sy + sx + sz]
+    corners = np.stack([cell + o for o in offs])
+    return p, corners, ne
+
+
+class MeshTri(Mesh):
+    elem = ElementTriP1
+    affine = True
+    sort_t = True
+
+    @staticmethod
+    def _default():
+        return (np.array([[0., 0.], [1., 0.], [0., 1.], [1., 1.]]).T,
+                np.array([[0, 1, 2], [1, 3, 2]]).T)
+
+    @classmethod
+    def init_tensor(cls, x, y):
+        npx, npy = len(x), len(y)
+        X, Y = np.meshgrid(np.sort(x), np.sort(y))
+        p = np.vstack((X.flatten('F'), Y.flatten('F')))
+        ix = np.arange(npx * npy, dtype=np.int64).reshape(npy, npx, order='F')
+        nt = (npx - 1) * (npy - 1)
+        c = ix[:-1, :-1].reshape(nt, order='F')
+        # two triangles per cell sharing the diagonal (corner 0 -> corner 3)
+        t = np.hstack((np.stack((c, c + 1, c + npy + 1)),
+                       np.stack((c, c + npy, c + npy + 1))))
+        return cls(p, t)
+
+    def _uniform(self):
+        """Red refinement: new vertices at facet (edge) midpoints."""
+        p, t, sz = self.p, self.t, self.p.shape[1]
+        mid = self.t2f + sz
+        newp = np.hstack((p, p[:, self.facets].mean(axis=1)))
+        newt = np.hstack((
+            np.vstack((t[0], mid[0], mid[2])),
+            np.vstack((t[1], mid[0], mid[1])),
+            np.vstack((t[2], mid[2], mid[1])),
+            np.vstack((mid[0], mid[1], mid[2])),
+        ))
+        return type(self)(newp, newt)
+
+
+class MeshTet(Mesh):
+    elem = ElementTetP1
+    affine = True
+
+    @staticmethod
+    def _default():
+        p = np.array([[0., 0., 0.], [0., 0., 1.], [0., 1., 0.], [1., 0., 0.],
+                      [0., 1., 1.], [1., 0., 1.], [1., 1., 0.], [1., 1., 1.]]).T
+        t = np.array([[0, 1, 2, 3], [3, 5, 1, 7], [2, 3, 6, 7], [2, 3, 1, 7],
+                      [1, 2, 4, 7]]).T
+        return p, t
+
+    @classmethod
+    def init_tensor(cls, x, y, z):
+        """Tensor-product grid, each cell split into the six Kuhn tetrahedra
+        that share the body diagonal (corner 0 -> corner 7); the element order
+        is type-major: all cells' first tet, then all second tets, ..."""
+        p, c, _ = _tensor_grid(x, y, z)
+        kuhn = ([0, 1, 5, 7], [0, 1, 4, 7], [0, 2, 4, 7],
+                [0, 3, 5, 7], [0, 2, 6, 7], [0, 3, 6, 7])
+        return cls(p, np.hstack([c[rows] for rows in kuhn]))
+
+
+class MeshHex(Mesh):
+    elem = ElementHex1
+    affine = False
+    _sort_facets = False    # hex facets keep their loop order (mesh_hex_1.py:49-55)
+
+    @staticmethod
+    def _default():
+        p = np.array([[0., 0., 0.], [0., 0., 1.], [0., 1., 0.], [1., 0., 0.],
+                      [0., 1., 1.], [1., 0., 1.], [1., 1., 0.], [1., 1., 1.]]).T
+        return p, np.arange(8).reshape(8, 1)
+
+    @classmethod
+    def init_tensor(cls, x, y, z):
+        p, c, _ = _tensor_grid(x, y, z)
+        return cls(p, c)
+
+
+MeshTri1, MeshTet1, MeshHex1 = MeshTri, MeshTet, MeshHex

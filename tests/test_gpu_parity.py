@@ -1,0 +1,176 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against (a) the golden
+vectors produced by the real reference and (b) the oracle on the same inputs.
+
+Bar (BASELINE.json north_star): DOF numbering, indptr and indices bit-exact;
+element-local data bit-exact (array_equal) wherever the arithmetic contract
+allows it; CSR values within rtol 1e-12 (+ atol 1e-12*max|A| for noise-level
+entries); load vectors bit-exact."""
+import numpy as np
+import pytest
+
+import skfem_b200 as fem
+from cases import CASES, LAME, load, mesh_of
+from product import forms, mesh_from, element_from
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _check_csr(A, g, f):
+    assert A.indptr.dtype == np.int32 and A.indices.dtype == np.int32
+    assert np.array_equal(A.indptr, g[f + "_indptr"]), f
+    assert np.array_equal(A.indices, g[f + "_indices"]), f
+    ref = g[f + "_data"]
+    np.testing.assert_allclose(A.data, ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_against_reference_golden(name):
+    refdom, ename, vector, bil, lin, has_local = CASES[name]
+    g = load(name)
+    b = fem.Basis(mesh_from(g, refdom), element_from(ename, vector))
+    fs = forms(vector)
+    for f in bil:
+        coo = fs[f].elemental(b)
+        traced_transcendental = False
+        if has_local:
+            assert np.array_equal(coo.data, g[f + "_local"]), (name, f)
+            assert np.array_equal(coo.indices.shape, (2, coo.data.shape[0]))
+        A = fs[f].assemble(b)
+        _check_csr(A, g, f)
+        assert A.has_canonical_format
+    for f in lin:
+        vec = fs[f].assemble(b)
+        if f == "user_load":  # np.sin: libdevice vs libm may differ in the last ulp
+            np.testing.assert_allclose(vec, g[f + "_vec"], rtol=1e-13, atol=1e-16)
+        else:
+            assert np.array_equal(vec, g[f + "_vec"]), (name, f)
+
+
+@pytest.mark.parametrize("name", ["hex2_tensor2", "hex2_morphed2"])
+def test_hex2_value_parity(name):
+    """Hex2 tables are tensor-product evaluated (not the reference's generated
+    Horner forms), so parity is value-level; the pattern has no exact zeros."""
+    g = load(name)
+    b = fem.Basis(mesh_from(g, "hex"), fem.ElementHex2())
+    fs = forms(False)
+    for f in ["laplace", "mass"]:
+        A = fs[f].assemble(b)
+        assert np.array_equal(A.indptr, g[f + "_indptr"])
+        assert np.array_equal(A.indices, g[f + "_indices"])
+        ref = g[f + "_data"]
+        np.testing.assert_allclose(A.data, ref, rtol=1e-11, atol=1e-13 * np.abs(ref).max())
+
+
+def test_known_answers():
+    # doctest of skfem/assembly/__init__.py:38-46
+    from skfem_b200.models.poisson import mass, unit_load, laplace
+    b = fem.Basis(fem.MeshTri(), fem.ElementTriP1())
+    M = mass.assemble(b).toarray()
+    ref = np.array([[0.08333333, 0.04166667, 0.04166667, 0.],
+                    [0.04166667, 0.16666667, 0.08333333, 0.04166667],
+                    [0.04166667, 0.08333333, 0.16666667, 0.04166667],
+                    [0., 0.04166667, 0.04166667, 0.08333333]])
+    np.testing.assert_allclose(M, ref, atol=1e-8)
+    np.testing.assert_allclose(unit_load.assemble(b), [1 / 6, 1 / 3, 1 / 3, 1 / 6], atol=1e-14)
+    # ex01 (README): solve the Poisson problem on MeshTri().refined(4)
+    from scipy.sparse.linalg import spsolve
+    b = fem.Basis(fem.MeshTri().refined(4), fem.ElementTriP1())
+    A, f = laplace.assemble(b), unit_load.assemble(b)
+    assert A.nnz == 1377 and A.shape == (289, 289)
+    I = b.complement_dofs(b.get_dofs())
+    x = np.zeros(b.N)
+    x[I] = spsolve(A[I][:, I].tocsc(), f[I])
+    gx = np.load(__import__("os").path.join(__import__("cases").GOLDEN, "ex01_solution.npz"))["x"]
+    np.testing.assert_allclose(x, gx, rtol=1e-10, atol=1e-14)
+    # closed-form nnz of the 7-point stencil
+    n = 12
+    b = fem.Basis(fem.MeshTet.init_tensor(*(3 * (np.linspace(0, 1, n + 1),))), fem.ElementTetP1())
+    assert laplace.assemble(b).nnz == (n + 1) ** 3 + 6 * n * (n + 1) ** 2
+
+
+def test_against_oracle_medium_sizes():
+    """Same seeded inputs, oracle vs CUDA, at sizes the oracle does in seconds."""
+    from oracle import skfem_oracle as O
+    from skfem_b200.models.poisson import laplace, mass, unit_load
+    rng = np.random.default_rng(7)
+    x = np.sort(rng.random(14)); y = np.sort(rng.random(12)); z = np.sort(rng.random(13))
+    m = fem.MeshTet.init_tensor(x, y, z)
+    p = m.p + 0.004 * rng.standard_normal(m.p.shape)      # unstructured geometry
+    m = fem.MeshTet(p, m.t)
+    mo = mesh_of(dict(p=m.p, t=m.t), "tet")
+    for ename, pe in (("tet_p1", fem.ElementTetP1()), ("tet_p2", fem.ElementTetP2())):
+        b = fem.Basis(m, pe)
+        bo = O.cell_basis(mo, O.element(ename))
+        assert np.array_equal(b.element_dofs, bo.element_dofs)
+        for form, oform in ((laplace, O.laplace), (mass, O.mass)):
+            idx, data, shape = O.bilinear_coo(oform, bo)
+            coo = form.elemental(b)
+            assert np.array_equal(coo.data, data)
+            assert np.array_equal(coo.indices, idx)
+            Ao = O.coo_to_csr(idx, data, shape)
+            A = form.assemble(b)
+            assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+            np.testing.assert_allclose(A.data, Ao.data, rtol=RTOL,
+                                       atol=RTOL * np.abs(Ao.data).max())
+        assert np.array_equal(unit_load.assemble(b), O.assemble_linear(O.unit_load, bo))
+
+
+def test_determinism_and_plan_reuse():
+    from skfem_b200.models.poisson import laplace
+    m = fem.MeshTet.init_tensor(*(3 * (np.linspace(0, 1, 17),)))
+    b = fem.Basis(m, fem.ElementTetP1())
+    A1 = laplace.assemble(b)            # cold: builds the plan
+    A2 = laplace.assemble(b)            # warm: reuses it
+    b2 = fem.Basis(m, fem.ElementTetP1())
+    A3 = laplace.assemble(b2)           # independent cold run
+    for B in (A2, A3):
+        assert np.array_equal(A1.indptr, B.indptr) and np.array_equal(A1.indices, B.indices)
+        assert np.array_equal(A1.data, B.data)   # bitwise: no float atomics anywhere
+
+
+def test_element_subset_and_edge_cases():
+    from skfem_b200.models.poisson import laplace, unit_load
+    from oracle import skfem_oracle as O
+    g = load("tet_p1_morphed5")
+    m = mesh_from(g, "tet")
+    sub = np.arange(5, 300, 7)
+    b = fem.Basis(m, fem.ElementTetP1(), elements=sub)
+    bo = O.cell_basis(mesh_of(g, "tet"), O.element("tet_p1"), elements=sub)
+    A, Ao = laplace.assemble(b), O.assemble_bilinear(O.laplace, bo)
+    assert A.shape == Ao.shape
+    assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+    np.testing.assert_allclose(A.data, Ao.data, rtol=RTOL, atol=RTOL * np.abs(Ao.data).max())
+    assert np.array_equal(unit_load.assemble(b), O.assemble_linear(O.unit_load, bo))
+    # empty element set
+    be = fem.Basis(m, fem.ElementTetP1(), elements=np.zeros(0, dtype=np.int32))
+    Ae = laplace.assemble(be)
+    assert Ae.nnz == 0 and Ae.shape == (b.N, b.N)
+    assert np.array_equal(unit_load.assemble(be), np.zeros(b.N))
+    # single element
+    b1 = fem.Basis(m, fem.ElementTetP1(), elements=[3])
+    bo1 = O.cell_basis(mesh_of(g, "tet"), O.element("tet_p1"), elements=np.array([3]))
+    A1, Ao1 = laplace.assemble(b1), O.assemble_bilinear(O.laplace, bo1)
+    assert np.array_equal(A1.indices, Ao1.indices) and np.array_equal(A1.data, Ao1.data)
+    # degenerate (zero-volume) element: affine map does not raise, inf/nan propagate
+    p = m.p.copy()
+    p[:, m.t[1, 0]] = p[:, m.t[0, 0]]
+    bd = fem.Basis(fem.MeshTet(p, m.t), fem.ElementTetP1(), elements=[0])
+    loc = laplace.elemental(bd).data
+    assert not np.isfinite(loc).all()
+    # zero Jacobian on a hex raises like the reference
+    gh = load("hex1_tensor3")
+    ph = gh["p"].copy()
+    ph[:] = 0.0
+    with pytest.raises(Exception, match="Zero Jacobian determinant"):
+        laplace.assemble(fem.Basis(fem.MeshHex(ph, gh["t"]), fem.ElementHex1()))
+
+
+def test_quadrature_mismatch_errors():
+    from skfem_b200.models.poisson import laplace
+    m = fem.MeshTri().refined(1)
+    b1 = fem.Basis(m, fem.ElementTriP1(), intorder=2)
+    b2 = fem.Basis(m, fem.ElementTriP1(), intorder=4)
+    with pytest.raises(ValueError, match="Quadrature mismatch"):
+        laplace.assemble(b1, b2)

@@ -1,0 +1,112 @@
+"""CPU tests of the host-side mirror: mesh constructors, topology, DOF
+numbering, quadrature and reference tables must be bit-identical to the
+reference's (golden vectors), and the C-ABI library must load and export every
+symbol the header declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import skfem_b200 as fem
+from cases import CASES, load
+from product import mesh_from, element_from
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_dofs_quadrature_tables_match_reference(name):
+    refdom, ename, vector, _, _, _ = CASES[name]
+    g = load(name)
+    m = mesh_from(g, refdom)
+    b = fem.Basis(m, element_from(ename, vector))
+    assert b.element_dofs.dtype == np.int32
+    assert np.array_equal(b.element_dofs, g["element_dofs"])
+    assert b.N == int(g["N"])
+    assert np.array_equal(b.X, g["X"]) and np.array_equal(b.W, g["W"])
+    assert np.array_equal(b._phi, g["phi"])
+    assert np.array_equal(b._dphi, g["dphi"])
+
+
+def test_mesh_constructors_match_reference():
+    g = load("c1_tri_p1_refined4")
+    m = fem.MeshTri().refined(4)
+    assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
+    assert m.t.dtype == np.int32 and m.p.dtype == np.float64
+    lin = np.linspace(0, 1, 7)
+    g = load("tet_p1_tensor6")
+    m = fem.MeshTet.init_tensor(lin, lin, lin)
+    assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
+    g = load("tet_p1_tensor_nonuniform")
+    lin = np.linspace
+    m = fem.MeshTet.init_tensor(lin(0, 1, 5) ** 2, lin(0, 1, 4), np.sqrt(lin(0, 1, 6)))
+    assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
+    g = load("hex1_tensor3")
+    m = fem.MeshHex.init_tensor(*(3 * (np.linspace(0, 1, 4),)))
+    assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
+    g = load("tri_p1_two_triangles")
+    m = fem.MeshTri()
+    assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
+
+
+def test_hex2_tables_close_to_reference():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hex2_tables.npz"))
+    e = fem.ElementHex2()
+    X, W = fem.get_quadrature(e.refdom, 2 * e.maxdeg)
+    assert np.array_equal(X, g["X"]) and np.array_equal(W, g["W"])
+    phi, dphi = e.tabulate(X)
+    np.testing.assert_allclose(phi, g["phi"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(dphi, g["dphi"], rtol=0, atol=2e-14)
+    b = fem.Basis(fem.MeshHex.init_tensor(*(3 * (np.linspace(0, 1, 3),))), e)
+    gg = load("hex2_tensor2")
+    assert np.array_equal(b.element_dofs, gg["element_dofs"]) and b.N == 125
+
+
+def test_incompatible_mesh_and_element():
+    with pytest.raises(ValueError, match="Incompatible Mesh and Element."):
+        fem.Basis(fem.MeshTri(), fem.ElementTetP1())
+
+
+def test_quadrature_unknown_order():
+    with pytest.raises(NotImplementedError):
+        fem.get_quadrature(fem.ElementTetP1().refdom, 50)
+
+
+def test_boundary_dofs():
+    m = fem.MeshTri().refined(2)
+    b = fem.Basis(m, fem.ElementTriP1())
+    D = b.get_dofs()
+    on_bnd = np.nonzero((m.p[0] == 0) | (m.p[0] == 1) | (m.p[1] == 0) | (m.p[1] == 1))[0]
+    assert np.array_equal(np.sort(D), on_bnd)
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "skfem_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(skb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from skfem_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 9
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), n
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in _lib.lib().skb_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from skfem_b200.models.poisson import laplace
+    b = fem.Basis(fem.MeshTri(), fem.ElementTriP1())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        laplace.assemble(b)

@@ -56,6 +56,12 @@ def dump(name, m, e, bil=(), lin_=(), store_local=True):
     b = fem.Basis(m, e)
     out = dict(p=m.p, t=m.t, element_dofs=b.element_dofs, N=np.int64(b.N),
                X=b.X, W=b.W, dx=b.dx if b.dx.size < 200000 else b.dx[:64])
+    es = e.elem if isinstance(e, fem.ElementVector) else e
+    nbs = b.Nbfun // (e.dim if isinstance(e, fem.ElementVector) else 1)
+    tabs = [es.lbasis(b.X, i) for i in range(nbs)]
+    out["phi"] = np.array([np.broadcast_to(t_[0], b.W.shape) for t_ in tabs])
+    out["dphi"] = np.array([t_[1] for t_ in tabs])
+    out["x"] = b.global_coordinates() if m.t.shape[1] < 3000 else np.zeros(0)
     for fname, form in bil:
         coo = form.elemental(b)
         A = coo.tocsr()
