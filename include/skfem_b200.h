@@ -132,10 +132,12 @@ int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *se
  * detabs: (nel, nqp) |detDF|.  Any output pointer may be NULL.             */
 int skb_tabulate(const skb_space_t *space, int b, double *grad, double *dx, double *x,
                  double *detabs, void *stream);
-/* out[e] = numpy-pairwise sum over q of integrand[e,q]*dx[e,q]
- * (bilinear_form.py:150-151; numpy pairwise_sum).                           */
+/* out[e] = sum over q of integrand[e,q]*dx[e,q] (bilinear_form.py:150-151) in
+ * numpy's order: pairwise (numpy pairwise_sum) when the product array is
+ * C-ordered, plain left-to-right (sequential != 0) when it is Fortran-ordered
+ * (the caller tracks the layout numpy would have produced).                 */
 int skb_qp_reduce(const double *integrand, const double *dx, int64_t nel, int32_t nqp,
-                  double *out, void *stream);
+                  int sequential, double *out, void *stream);
 
 /* library / build identification */
 const char *skb_version(void);

@@ -208,4 +208,15 @@ __device__ double pw_sum(int n, F &f) {
   return ret;
 }
 
+// Plain left-to-right sum.  numpy reduces this way when the (nel, nqp) operand
+// of np.sum(axis=1) is Fortran-ordered (the reduction axis is then the outer
+// loop): e.g. ``v * dx`` for an affine mesh, where dx = np.tile(detA, (nqp,1)).T
+// is F-ordered and v is a stride-0 broadcast (DESIGN.md "layout rule").
+template <class F>
+__device__ __forceinline__ double seq_sum(int n, F &f) {
+  double r = f(0);
+  for (int i = 1; i < n; ++i) r = r + f(i);
+  return r;
+}
+
 }  // namespace skb

@@ -142,14 +142,16 @@ local_affine_kernel(const skb_space_t s, int form, double lambda, double two_mu,
     affine_invert(g);
     const double absdet = fabs(g.det);
     if (!BILINEAR) {
-      // LinearForm._assemble (linear_form.py:41-44), unit_load: v
+      // LinearForm._assemble (linear_form.py:41-44), unit_load: v.
+      // v is a stride-0 broadcast and the affine dx is Fortran-ordered, so
+      // numpy's v*dx is F-ordered and np.sum(axis=1) adds left to right.
       for (int ib = 0; ib < nbs; ++ib)
         for (int nv = 0; nv < NC; ++nv) {
           auto f = [&](int q) -> double {
             double dx = absdet * tab.W[q];
             return tab.phi[ib * nqp + q] * dx;
           };
-          out[(int64_t)(ib * NC + nv) * s.nel + e] = pw_sum(nqp, f);
+          out[(int64_t)(ib * NC + nv) * s.nel + e] = seq_sum(nqp, f);
         }
       continue;
     }
@@ -281,8 +283,9 @@ static int grid_for(int64_t work_items, int block, int per_sm) {
 template <bool BILINEAR>
 static int launch_local(const skb_space_t *sp, int form, const double *params, double *out,
                         cudaStream_t st) {
-  if (!sp || !out || sp->nel < 0) return SKB_EINVAL;
+  if (!sp || sp->nel < 0) return SKB_EINVAL;
   if (sp->nel == 0) return SKB_OK;
+  if (!out) return SKB_EINVAL;
   const skb_space_t s = *sp;
   const bool vec = s.ncomp > 1;
   if (vec && s.ncomp != s.dim) return SKB_EINVAL;

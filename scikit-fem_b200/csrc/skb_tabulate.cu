@@ -110,12 +110,12 @@ tabulate_hex_kernel(const skb_space_t s, int b, double *__restrict__ grad, doubl
 
 __global__ void __launch_bounds__(128)
 qp_reduce_kernel(const double *__restrict__ integrand, const double *__restrict__ dx, int64_t nel,
-                 int nqp, double *__restrict__ out) {
+                 int nqp, int sequential, double *__restrict__ out) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nel;
        e += (int64_t)gridDim.x * blockDim.x) {
     const double *a = integrand + e * nqp, *d = dx + e * nqp;
     auto f = [&](int q) -> double { return a[q] * d[q]; };
-    out[e] = pw_sum(nqp, f);
+    out[e] = sequential ? seq_sum(nqp, f) : pw_sum(nqp, f);
   }
 }
 
@@ -163,11 +163,11 @@ extern "C" int skb_tabulate(const skb_space_t *space, int b, double *grad, doubl
 }
 
 extern "C" int skb_qp_reduce(const double *integrand, const double *dx, int64_t nel, int32_t nqp,
-                             double *out, void *stream) {
+                             int sequential, double *out, void *stream) {
   using namespace skb;
   if (nel < 0 || nqp <= 0) return SKB_EINVAL;
   if (nel == 0) return SKB_OK;
-  qp_reduce_kernel<<<nblk(nel, 128), 128, 0, (cudaStream_t)stream>>>(integrand, dx, nel, nqp, out);
+  qp_reduce_kernel<<<nblk(nel, 128), 128, 0, (cudaStream_t)stream>>>(integrand, dx, nel, nqp, sequential, out);
   return (int)cudaGetLastError();
 }
 

@@ -255,7 +255,8 @@ class CellBasis(AbstractBasis):
         g = self._scalar_grad_dev(b)
         val = d["phi"][b].expand(nel, nqp)
         if nc == 1:
-            return DiscreteField(val, g)
+            # numpy: value is a stride-0 broadcast of phi (element_h1.py:15)
+            return DiscreteField(val, g, lay="B")
         vv = torch.zeros((dim, nel, nqp), dtype=torch.float64, device=d["device"])
         gg = torch.zeros((dim, dim, nel, nqp), dtype=torch.float64, device=d["device"])
         vv[n] = val
@@ -279,7 +280,14 @@ class CellBasis(AbstractBasis):
         if "h" not in self._fields:
             det = self._tabulate(want=("detabs",))["detabs"]
             self._fields["h"] = det ** (1. / self.mesh.dim())
-        return DiscreteField(self._fields["h"])
+        return DiscreteField(self._fields["h"], lay=self._dx_layout)
+
+    @property
+    def _dx_layout(self):
+        """numpy layout of the reference's ``dx``: MappingAffine.detDF is
+        ``np.tile(detA, (nqp, 1)).T`` (mapping_affine.py:205-211), i.e.
+        Fortran-ordered; the isoparametric one is C-ordered."""
+        return "F" if self._affine else "C"
 
     def default_parameters(self):
         """``w.x`` and ``w.h`` (cell_basis.py:124-141) as device fields."""

@@ -103,14 +103,40 @@ def _stack(seq):
     return DeviceArray(torch.stack([i.expand(shape) for i in items]))
 
 
+def combine_layout(lays):
+    """Memory order numpy would give the result of an elementwise op.
+
+    numpy allocates ufunc outputs in 'K' order: C order wins any conflict, an
+    operand whose element axis has stride 0 (a broadcast basis value, 'B') has
+    no say, Fortran order ('F', e.g. the affine ``dx``) survives only if no
+    C-ordered operand takes part (nditer's axis-ordering rule).  The order
+    matters because ``np.sum(axis=1)`` is pairwise on C-ordered data and plain
+    left-to-right on F-ordered data ("layout rule")."""
+    lays = [x for x in lays if x is not None]
+    if "C" in lays:
+        return "C"
+    if "F" in lays:
+        return "F"
+    return "C"
+
+
+def layout_of(x):
+    return x.lay if isinstance(x, DeviceArray) else None
+
+
 class DeviceArray:
     """A float64 CUDA tensor speaking enough of the ndarray protocol for form
-    definitions."""
+    definitions.  ``lay`` tracks the memory order ('C', 'F' or 'B'roadcast) the
+    equivalent numpy array would have; the device data itself is always
+    C-ordered."""
     __array_priority__ = 1000.0
-    __slots__ = ("t",)
+    __slots__ = ("t", "lay")
 
-    def __init__(self, t):
-        self.t = t.t if isinstance(t, DeviceArray) else t
+    def __init__(self, t, lay="C"):
+        if isinstance(t, DeviceArray):
+            t, lay = t.t, t.lay
+        self.t = t
+        self.lay = lay
 
     # -- ndarray-like attributes -------------------------------------------------
     @property
@@ -172,7 +198,8 @@ class DeviceArray:
         o = raw(other)
         if o is NotImplemented:
             return NotImplemented
-        return DeviceArray(fn(o, self.t) if swap else fn(self.t, o))
+        return DeviceArray(fn(o, self.t) if swap else fn(self.t, o),
+                           combine_layout([self.lay, layout_of(other)]))
 
     def __add__(self, o): return self._bin(o, torch.add)
     def __radd__(self, o): return self._bin(o, torch.add, True)
@@ -184,9 +211,9 @@ class DeviceArray:
     def __rtruediv__(self, o): return self._bin(o, lambda a, b: torch.div(torch.as_tensor(a, dtype=b.dtype, device=b.device), b), True)
     def __pow__(self, o): return self._bin(o, _power)
     def __rpow__(self, o): return self._bin(o, lambda a, b: torch.pow(torch.as_tensor(a, dtype=b.dtype, device=b.device), b), True)
-    def __neg__(self): return DeviceArray(torch.neg(self.t))
-    def __pos__(self): return DeviceArray(self.t)
-    def __abs__(self): return DeviceArray(torch.abs(self.t))
+    def __neg__(self): return DeviceArray(torch.neg(self.t), combine_layout([self.lay]))
+    def __pos__(self): return DeviceArray(self.t, self.lay)
+    def __abs__(self): return DeviceArray(torch.abs(self.t), combine_layout([self.lay]))
     def __lt__(self, o): return self._bin(o, torch.lt)
     def __le__(self, o): return self._bin(o, torch.le)
     def __gt__(self, o): return self._bin(o, torch.gt)
@@ -199,17 +226,18 @@ class DeviceArray:
         name = ufunc.__name__
         args = [raw(a) for a in inputs]
         ref = _like(inputs)
+        lay = combine_layout([layout_of(a) for a in inputs])
         if name in _UNARY and len(args) == 1:
-            return DeviceArray(_UNARY[name](args[0]))
+            return DeviceArray(_UNARY[name](args[0]), lay)
         if name in _BINARY and len(args) == 2:
             fn = _BINARY[name]
             if name in ("power", "float_power"):
                 if not torch.is_tensor(args[0]):
                     args[0] = torch.as_tensor(args[0], dtype=ref.dtype, device=ref.device)
-                return DeviceArray(fn(args[0], args[1]))
+                return DeviceArray(fn(args[0], args[1]), lay)
             args = [a if torch.is_tensor(a) else torch.as_tensor(a, dtype=ref.dtype, device=ref.device)
                     for a in args]
-            return DeviceArray(fn(*args))
+            return DeviceArray(fn(*args), lay)
         raise NotImplementedError("numpy ufunc '{}' is not available on device fields".format(name))
 
     def __array_function__(self, func, types, args, kwargs):
@@ -229,8 +257,8 @@ class DiscreteField(DeviceArray):
     _extra_attrs = ("grad", "div", "curl", "hess", "grad3", "grad4", "grad5", "grad6")
 
     def __init__(self, value=None, grad=None, div=None, curl=None, hess=None,
-                 grad3=None, grad4=None, grad5=None, grad6=None):
-        super().__init__(value)
+                 grad3=None, grad4=None, grad5=None, grad6=None, lay="C"):
+        super().__init__(value, lay)
 
         def wrap(a):
             return None if a is None else (a if isinstance(a, DeviceArray) else DeviceArray(a))
@@ -240,7 +268,7 @@ class DiscreteField(DeviceArray):
 
     def get(self, n):
         if n == 0:
-            return DeviceArray(self.t)
+            return DeviceArray(self.t, self.lay)
         return getattr(self, self._extra_attrs[n - 1])
 
     @property
@@ -249,7 +277,7 @@ class DiscreteField(DeviceArray):
 
     @property
     def value(self):
-        return DeviceArray(self.t)
+        return DeviceArray(self.t, self.lay)
 
     def zeros(self):
         return DiscreteField(*tuple(None if c is None else torch.zeros_like(c.t)

@@ -34,7 +34,7 @@ from typing import Any, Optional, Tuple
 import numpy as np
 
 from . import _lib
-from .field import DeviceArray, DiscreteField
+from .field import DeviceArray, DiscreteField, combine_layout, layout_of
 
 logger = logging.getLogger(__name__)
 
@@ -301,8 +301,11 @@ class Form:
         if t.dtype != torch.float64:
             t = t.to(torch.float64)
         t = t.expand(nel, nqp).contiguous()
+        # np.sum(form * dx, axis=1): pairwise if numpy's product is C-ordered,
+        # left-to-right if it is Fortran-ordered (field.combine_layout)
+        seq = combine_layout([layout_of(integrand), basis._dx_layout]) == "F"
         code = _lib.lib().skb_qp_reduce(t.data_ptr(), basis._dx_dev().data_ptr(), nel, nqp,
-                                        out_row.data_ptr(), _stream())
+                                        1 if seq else 0, out_row.data_ptr(), _stream())
         _lib.check(code, "skb_qp_reduce")
 
     def assemble(self, *args, **kwargs) -> Any:

@@ -27,8 +27,9 @@ CASES = {
                         ["unit_load"], True),
     "tet_p2_tensor3": ("tet", "tet_p2", False, ["laplace", "mass"],
                        ["unit_load"], True),
-    "tet_p2_morphed3": ("tet", "tet_p2", False, ["laplace", "mass"],
-                        ["unit_load"], True),
+    "tet_p2_morphed3": ("tet", "tet_p2", False,
+                        ["laplace", "mass", "user_aniso"],
+                        ["unit_load", "user_load"], True),
     "tet_vp2_elasticity2": ("tet", "tet_p2", True,
                             ["elasticity", "vector_laplace"], [], True),
     "tet_vp2_elasticity_morphed2": ("tet", "tet_p2", True, ["elasticity"], [],

@@ -117,8 +117,9 @@ dump("tet_p2_tensor3", fem.MeshTet.init_tensor(lin(4), lin(4), lin(4)),
      lin_=[("unit_load", unit_load)])
 m3 = fem.MeshTet.init_tensor(lin(4), lin(4), lin(4))
 dump("tet_p2_morphed3", fem.MeshTet(morph_pts(m3.p), m3.t),
-     fem.ElementTetP2(), bil=[("laplace", laplace), ("mass", mass)],
-     lin_=[("unit_load", unit_load)])
+     fem.ElementTetP2(),
+     bil=[("laplace", laplace), ("mass", mass), ("user_aniso", user_aniso)],
+     lin_=[("unit_load", unit_load), ("user_load", user_load)])
 # C3 shape, small: vector P2 elasticity (+ vector P1 variants)
 dump("tet_vp2_elasticity2", fem.MeshTet.init_tensor(lin(3), lin(3), lin(3)),
      fem.ElementVector(fem.ElementTetP2()),
