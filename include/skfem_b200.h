@@ -139,6 +139,10 @@ int skb_tabulate(const skb_space_t *space, int b, double *grad, double *dx, doub
 int skb_qp_reduce(const double *integrand, const double *dx, int64_t nel, int32_t nqp,
                   int sequential, double *out, void *stream);
 
+/* number of kernels of this library launched so far by this process (the
+ * bench's `gpu_launches`); reset != 0 zeroes the counter after reading.     */
+int64_t skb_launch_count(int reset);
+
 /* library / build identification */
 const char *skb_version(void);
 

@@ -555,20 +555,36 @@ class _W(dict):
         return self[k]
 
 
-def bilinear_coo(form, basis, **kw):
-    """BilinearForm._assemble (assembly/form/bilinear_form.py:58-128)."""
+def bilinear_coo(form, basis, nthreads=0, **kw):
+    """BilinearForm._assemble (assembly/form/bilinear_form.py:58-128);
+    ``nthreads > 0`` restates the reference's Python-thread split of the
+    Nbfun^2 loop (:100-119,153-161)."""
     nt, nb = basis.nelems, basis.Nbfun
     w = _W(x=basis.x, h=basis.h, **kw)
     data = np.zeros((nb, nb, nt))
     rows = np.zeros(nb * nb * nt, dtype=np.int32)
     cols = np.zeros(nb * nb * nt, dtype=np.int32)
+
+    def kernel(j, i):
+        data[j, i, :] = np.sum(form(basis.basis[j], basis.basis[i], w)
+                               * basis.dx, axis=1)         # :150-151
+
     for j in range(nb):
         for i in range(nb):
             ixs = slice(nt * (nb * j + i), nt * (nb * j + i + 1))
             rows[ixs] = basis.element_dofs[i]
             cols[ixs] = basis.element_dofs[j]
-            data[j, i, :] = np.sum(form(basis.basis[j], basis.basis[i], w)
-                                   * basis.dx, axis=1)     # :150-151
+            if nthreads <= 0:
+                kernel(j, i)
+    if nthreads > 0:
+        from threading import Thread
+        pairs = np.array([[i, j] for j in range(nb) for i in range(nb)])
+        threads = [Thread(target=lambda ix: [kernel(j, i) for i, j in ix], args=(ix,))
+                   for ix in np.array_split(pairs, nthreads, axis=0)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
     return np.array([rows, cols]), data.flatten('C'), (basis.N, basis.N)
 
 

@@ -22,6 +22,10 @@
 
 namespace skb {
 
+// kernel-launch accounting (skb_launch_count): every launcher reports how many
+// kernels of this library it enqueued
+void count_launch(int n = 1);
+
 // ---------------------------------------------------------------------------
 // Correctly rounded a/b for many numerators sharing one denominator.
 // y = RN(1/b) (__drcp_rn), q0 = RN(a*y), then Markstein corrections

@@ -310,6 +310,7 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
       SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                         (int)smem));                                         \
     k<<<grid, block, smem, st>>>(s, form, lambda, two_mu, out);                              \
+    count_launch();                                                                          \
   } while (0)
     if (s.dim == 2 && !vec) SKB_LAUNCH_AFFINE(2, false);
     else if (s.dim == 2 && vec) SKB_LAUNCH_AFFINE(2, true);
@@ -331,6 +332,7 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
       SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_for(s.nel * 256, 256, 8);
     k<<<grid, 256, smem, st>>>(s, form, out, err);
+    count_launch();
     int herr = 0;
     SKB_CUDA_TRY(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     SKB_CUDA_TRY(cudaStreamSynchronize(st));

@@ -170,6 +170,7 @@ extern "C" int skb_plan_symbolic(const int32_t *dofs_v, const int32_t *dofs_u, i
                                                        (uint64_t)ncols, sentinel, local_or_null,
                                                        drop_zeros, keys_a, vals_a);
   SKB_CUDA_TRY(cudaGetLastError());
+  count_launch(3);  // make_keys, head_flags, counts (CUB sort/scan passes not counted)
   unsigned long long *counts_dev = (unsigned long long *)tmp;
   void *cub_tmp = (char *)tmp + 256;
   size_t cub_bytes = (size_t)tmp_bytes - 256;
@@ -208,6 +209,7 @@ extern "C" int skb_plan_finalize(int64_t ncoo, int64_t nrows, int64_t ncols, int
   finalize_kernel<<<nblocks(nkeep + 1, 256), 256, 0, st>>>(keys_sorted, vals_sorted, slot, nkeep,
                                                            nnz, nrows, (uint64_t)ncols, indptr,
                                                            indices, segptr, perm);
+  count_launch();
   return (int)cudaGetLastError();
 }
 
@@ -218,6 +220,7 @@ extern "C" int skb_csr_reduce(const double *local, const uint32_t *perm, const u
   if (nnz == 0) return SKB_OK;
   csr_reduce_kernel<<<nblocks(nnz, 256), 256, 0, (cudaStream_t)stream>>>(local, perm, segptr, nnz,
                                                                          data);
+  count_launch();
   return (int)cudaGetLastError();
 }
 
@@ -228,5 +231,6 @@ extern "C" int skb_vec_reduce(const double *local, const uint32_t *perm, const u
   if (nrows == 0) return SKB_OK;
   vec_reduce_kernel<<<nblocks(nrows, 256), 256, 0, (cudaStream_t)stream>>>(local, perm, segptr,
                                                                            indptr, nrows, vec);
+  count_launch();
   return (int)cudaGetLastError();
 }

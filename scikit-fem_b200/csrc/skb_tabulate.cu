@@ -9,9 +9,13 @@
 //                                                    mapping_isoparametric.py:52-58,170-171
 //   detabs (nel, nqp)     |detDF| (for w.h)          cell_basis.py:136-141
 // plus the numpy-order quadrature reduction of bilinear_form.py:150-151.
+#include <atomic>
 #include "skb_common.cuh"
 
 namespace skb {
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
@@ -144,6 +148,7 @@ extern "C" int skb_tabulate(const skb_space_t *space, int b, double *grad, doubl
       tabulate_affine_kernel<3><<<nblk(s.nel, 128), 128, 0, st>>>(s, b, grad, dx, x, detabs);
     else
       return SKB_EINVAL;
+    count_launch();
     return (int)cudaGetLastError();
   }
   if (s.mapping == SKB_MAP_ISO_HEX1) {
@@ -152,6 +157,7 @@ extern "C" int skb_tabulate(const skb_space_t *space, int b, double *grad, doubl
     SKB_CUDA_TRY(cudaMallocAsync((void **)&err, sizeof(int), st));
     SKB_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
     tabulate_hex_kernel<<<nblk(s.nel * s.nqp, 128), 128, 0, st>>>(s, b, grad, dx, x, detabs, err);
+    count_launch();
     int herr = 0;
     SKB_CUDA_TRY(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     SKB_CUDA_TRY(cudaStreamSynchronize(st));
@@ -168,7 +174,14 @@ extern "C" int skb_qp_reduce(const double *integrand, const double *dx, int64_t 
   if (nel < 0 || nqp <= 0) return SKB_EINVAL;
   if (nel == 0) return SKB_OK;
   qp_reduce_kernel<<<nblk(nel, 128), 128, 0, (cudaStream_t)stream>>>(integrand, dx, nel, nqp, sequential, out);
+  count_launch();
   return (int)cudaGetLastError();
+}
+
+extern "C" int64_t skb_launch_count(int reset) {
+  long long v = skb::g_launches.load();
+  if (reset) skb::g_launches.store(0);
+  return (int64_t)v;
 }
 
 extern "C" const char *skb_version(void) { return "skfem_b200 0.1 (sm_100a, fmad=off)"; }

@@ -174,7 +174,7 @@ class CellBasis(AbstractBasis):
         def up(a, dtype=None):
             a = np.ascontiguousarray(a)
             return torch.from_numpy(a).to(device)
-        d["edofs"] = up(self.element_dofs)
+        d["edofs"] = t if self.element_dofs is self.mesh.t else up(self.element_dofs)
         d["phi"], d["dphi"], d["W"], d["X"] = up(self._phi), up(self._dphi), up(self.W), up(self.X)
         d["tind"] = None if self.tind is None else up(self.tind.astype(np.int32))
         if not self._affine:

@@ -45,14 +45,31 @@ class Dofs:
 
         self.interior_dofs = _block(element.interior_dofs, nel, offset)
 
-        parts = [self.nodal_dofs[:, topo.t[k]] for k in range(topo.t.shape[0])]
+        # nodal rows: nodal_dofs[c, v] == nd*v + c + offset0, so the gather
+        # nodal_dofs[:, t[k]] is plain integer arithmetic on t (and for one
+        # DOF per vertex element_dofs IS t: no copy, no extra upload)
+        nd, off0 = element.nodal_dofs, np.int32(self.nodal_dofs[0, 0]) if self.nodal_dofs.size else 0
+        self.nodal_is_t = False
+        if nd == 1 and off0 == 0:
+            parts = [topo.t]
+            self.nodal_is_t = True
+        else:
+            parts = [np.int32(nd) * topo.t[k][None, :]
+                     + (np.arange(nd, dtype=np.int32) + off0)[:, None]
+                     for k in range(topo.t.shape[0])] if nd > 0 else []
         if self.edge_dofs.size:
             parts += [self.edge_dofs[:, topo.t2e[k]] for k in range(topo.t2e.shape[0])]
         if element.dim >= 2 and self.facet_dofs.size:
             parts += [self.facet_dofs[:, topo.t2f[k]] for k in range(topo.t2f.shape[0])]
-        parts.append(self.interior_dofs)
-        self.element_dofs = np.ascontiguousarray(np.vstack(parts), dtype=np.int32)
-        self.N = int(np.max(self.element_dofs)) + 1
+        if self.interior_dofs.size:
+            parts.append(self.interior_dofs)
+        if len(parts) == 1 and self.nodal_is_t:
+            self.element_dofs = topo.t
+        else:
+            self.nodal_is_t = False
+            self.element_dofs = np.ascontiguousarray(np.vstack(parts), dtype=np.int32)
+        # == max(element_dofs) + 1: every vertex/edge/facet/cell is referenced
+        self.N = int(offset + self.interior_dofs.size)
 
     def boundary(self):
         """All DOFs attached to boundary vertices / edges / facets."""

@@ -69,8 +69,15 @@ class DeviceCSR:
 
     def to_scipy(self):
         from scipy.sparse import csr_matrix
-        A = csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
-                        self.indptr.cpu().numpy()), shape=self.shape)
+        torch = _torch()
+
+        def d2h(t):  # pinned staging + async copy: the three arrays overlap
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            return h
+        hd, hi, hp = d2h(self.data), d2h(self.indices), d2h(self.indptr)
+        torch.cuda.current_stream().synchronize()
+        A = csr_matrix((hd.numpy(), hi.numpy(), hp.numpy()), shape=self.shape, copy=False)
         A.has_sorted_indices = True
         A.has_canonical_format = True
         return A
