@@ -125,6 +125,26 @@ int skb_csr_reduce(const double *local, const uint32_t *perm, const uint32_t *se
 int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *segptr,
                    const int32_t *indptr, int64_t nrows, double *vec, void *stream);
 
+/* ---- fused P1 path (headline): ElementTetP1 Laplace straight to CSR values ----
+ * One pass replaces CellBasis.__init__ (cell_basis.py:94-106),
+ * BilinearForm._assemble (bilinear_form.py:58-128,150-151) and the value part of
+ * COOData._assemble_scipy_csr (coo_data.py:27-36): local matrices are formed
+ * in registers (bit-identical to numpy), staged in shared memory and reduced
+ * per CSR slot inside the CTA; they never reach HBM.  The tile plan (tt,
+ * tile_slot_start, tile_contrib_start, slot_ptr, contrib, meta, sptr, gslot)
+ * is built once per (mesh, pattern): see skfem_b200/fused.py for its layout.
+ * tile_elems must be 1024 or 2048.  w = the common quadrature weight (all
+ * weights of the rule must be equal), nqp = number of quadrature points.
+ * skb_p1_combine adds, in tile order, the per-tile partial sums of CSR slots
+ * touched by more than one tile.  No float atomics: bit-reproducible.        */
+int skb_p1tet_laplace_fused(const double *p, int64_t npts, const int32_t *tt, int32_t ntiles,
+                            int32_t tile_elems, const uint32_t *tile_slot_start,
+                            const uint32_t *tile_contrib_start, const uint16_t *slot_ptr,
+                            const uint16_t *contrib, const uint32_t *meta, double w, int32_t nqp,
+                            double *csr_data, double *scratch, void *stream);
+int skb_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
+                   int64_t nshared, double *csr_data, void *stream);
+
 /* ---- materialised basis for traced (user-defined) forms -----------------
  * grad: (dim, nel, nqp) of scalar basis function b (element_h1.py:17);
  * dx: (nel, nqp) (cell_basis.py:104-105); x: (dim, nel, nqp)

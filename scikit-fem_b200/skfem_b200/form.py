@@ -44,6 +44,26 @@ def _torch():
     return torch
 
 
+_CONFIG = {"fused": True, "fused_tile": 1024}
+
+
+def set_options(**kw):
+    """Engine switches: ``fused`` (use the fused P1 path for warm re-assembly),
+    ``fused_tile`` (elements per tile: 1024 or 2048)."""
+    for k, v in kw.items():
+        if k not in _CONFIG:
+            raise KeyError(k)
+        _CONFIG[k] = v
+
+
+def use_fused():
+    return bool(_CONFIG["fused"])
+
+
+def fused_tile():
+    return int(_CONFIG["fused_tile"])
+
+
 class FormExtraParams(dict):
     """Passed to forms as 'w'."""
 
@@ -378,9 +398,24 @@ class BilinearForm(Form):
         assert self.form is not None
         torch = _torch()
         vb = ubasis if vbasis is None else vbasis
-        local = self._local(ubasis, vbasis, **kwargs)
         key = self._plan_key(ubasis, vbasis, kwargs)
         plan = ubasis._plans.get(key) if key is not None else None
+        # warm re-assembly of a fusable form: geometry -> CSR values in one
+        # pass (csrc/skb_p1_fused.cu); the tile plan is built on the first
+        # warm call from the pattern the cold call established
+        if (plan is not None and vbasis is None and not kwargs and use_fused()
+                and ubasis.nelems > 0 and plan.nnz > 0):
+            from . import fused
+            if fused.applicable(ubasis, self):
+                fkey = ("fused", key)
+                fp = ubasis._plans.get(fkey)
+                if fp is None:
+                    fp = fused.build(ubasis, plan, T=fused_tile())
+                    ubasis._plans[fkey] = fp
+                data = torch.empty(plan.nnz, dtype=torch.float64, device=fp.p.device)
+                fused.run(fp, data, _stream())
+                return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
+        local = self._local(ubasis, vbasis, **kwargs)
         if plan is None:
             plan = build_plan(vb._dev()["edofs"], ubasis._dev()["edofs"], ubasis.nelems,
                               (vb.N, ubasis.N), local, drop_zeros=True)

@@ -118,16 +118,25 @@ def test_against_oracle_medium_sizes():
 
 
 def test_determinism_and_plan_reuse():
-    from skfem_b200.models.poisson import laplace
+    """Bit-reproducibility: each path (cold generic / warm fused) returns the
+    same bits every time; the two paths add in different orders and agree
+    within rtol 1e-12."""
+    from skfem_b200.models.poisson import laplace, mass
     m = fem.MeshTet.init_tensor(*(3 * (np.linspace(0, 1, 17),)))
     b = fem.Basis(m, fem.ElementTetP1())
-    A1 = laplace.assemble(b)            # cold: builds the plan
-    A2 = laplace.assemble(b)            # warm: reuses it
+    A1 = laplace.assemble(b)            # cold: builds the plan (generic path)
+    A2 = laplace.assemble(b)            # warm: fused path
+    A2b = laplace.assemble(b)
     b2 = fem.Basis(m, fem.ElementTetP1())
     A3 = laplace.assemble(b2)           # independent cold run
-    for B in (A2, A3):
+    A4 = laplace.assemble(b2)
+    for B in (A2, A3, A4):
         assert np.array_equal(A1.indptr, B.indptr) and np.array_equal(A1.indices, B.indices)
-        assert np.array_equal(A1.data, B.data)   # bitwise: no float atomics anywhere
+    assert np.array_equal(A1.data, A3.data)      # cold == cold, bitwise
+    assert np.array_equal(A2.data, A2b.data) and np.array_equal(A2.data, A4.data)  # warm == warm
+    np.testing.assert_allclose(A2.data, A1.data, rtol=RTOL, atol=RTOL * np.abs(A1.data).max())
+    M1, M2 = mass.assemble(b), mass.assemble(b)  # generic warm path reuses the plan
+    assert np.array_equal(M1.data, M2.data)
 
 
 def test_element_subset_and_edge_cases():
@@ -174,3 +183,53 @@ def test_quadrature_mismatch_errors():
     b2 = fem.Basis(m, fem.ElementTriP1(), intorder=4)
     with pytest.raises(ValueError, match="Quadrature mismatch"):
         laplace.assemble(b1, b2)
+
+
+@pytest.mark.parametrize("tile", [1024, 2048])
+def test_fused_p1_path(tile):
+    """Warm re-assembly goes through the fused kernel (csrc/skb_p1_fused.cu):
+    same plan (indptr/indices bit-exact), values within rtol 1e-12 of the
+    reference, bit-identical between repeated runs."""
+    from skfem_b200.models.poisson import laplace
+    from skfem_b200 import form as F
+    F.set_options(fused=True, fused_tile=tile)
+    try:
+        for name in ["tet_p1_tensor6", "tet_p1_ball2", "tet_p1_refined3", "tet_p1_morphed5",
+                     "tet_p1_tensor_nonuniform"]:
+            g = load(name)
+            b = fem.Basis(mesh_from(g, "tet"), fem.ElementTetP1())
+            A0 = laplace.assemble(b)                      # cold, generic path
+            A1 = laplace.assemble(b)                      # warm, fused path
+            assert ("fused", laplace._plan_key(b, None, {})) in b._plans
+            A2 = laplace.assemble(b)
+            _check_csr(A1, g, "laplace")
+            assert np.array_equal(A1.data, A2.data)
+            np.testing.assert_allclose(A1.data, A0.data, rtol=RTOL,
+                                       atol=RTOL * np.abs(A0.data).max())
+        # a mesh with several tiles and many shared slots
+        from oracle import skfem_oracle as O
+        rng = np.random.default_rng(3)
+        x = np.sort(rng.random(21)); y = np.sort(rng.random(19)); z = np.sort(rng.random(20))
+        m = fem.MeshTet.init_tensor(x, y, z)
+        m = fem.MeshTet(m.p + 0.002 * rng.standard_normal(m.p.shape), m.t)
+        b = fem.Basis(m, fem.ElementTetP1())
+        laplace.assemble(b)
+        A = laplace.assemble(b)
+        Ao = O.assemble_bilinear(O.laplace, O.cell_basis(mesh_of(dict(p=m.p, t=m.t), "tet"),
+                                                         O.element("tet_p1")))
+        assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+        np.testing.assert_allclose(A.data, Ao.data, rtol=RTOL, atol=RTOL * np.abs(Ao.data).max())
+        fp = b._plans[("fused", laplace._plan_key(b, None, {}))]
+        assert fp.ntiles == -(-m.nelements // tile) and fp.nshared > 0
+        # element subset
+        sub = np.arange(0, m.nelements, 3)
+        bs = fem.Basis(m, fem.ElementTetP1(), elements=sub)
+        laplace.assemble(bs)
+        As = laplace.assemble(bs)
+        Aso = O.assemble_bilinear(O.laplace, O.cell_basis(mesh_of(dict(p=m.p, t=m.t), "tet"),
+                                                          O.element("tet_p1"), elements=sub))
+        assert np.array_equal(As.indices, Aso.indices)
+        np.testing.assert_allclose(As.data, Aso.data, rtol=RTOL,
+                                   atol=RTOL * np.abs(Aso.data).max())
+    finally:
+        F.set_options(fused=True, fused_tile=1024)
