@@ -152,6 +152,8 @@ def run_gpu(args):
     from skfem_b200 import _lib
     from skfem_b200.models.poisson import laplace
 
+    from skfem_b200 import form as _form
+    _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads)
     cells = args.cells
     x = np.linspace(0, 1, cells + 1)
     if world == 1:
@@ -239,6 +241,12 @@ def run_gpu(args):
 
     peak, peak_src = peaks()
     nverts = m.p.shape[1]
+    fused_stats = None
+    for k, v in basis._plans.items():
+        if isinstance(k, tuple) and k and k[0] == "fused":
+            from skfem_b200 import fused as _fused
+            fused_stats = _fused.stats(v)
+            fused_stats["tile"], fused_stats["threads"] = v.T, v.threads
     algo_bytes = 4 * 4 * nel + 8 * 3 * nverts + 8 * nnz   # t + p + CSR data (warm)
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
     line = {
@@ -251,7 +259,8 @@ def run_gpu(args):
                                "(BASELINE configs[1]) warm re-assembly into CSR".format(cells + 1),
                    "elements_per_gpu": nel, "dofs_per_gpu": basis.N, "nnz_per_gpu": nnz,
                    "l2": "no flush: per-step working set (t, local data, plan) exceeds the 126 MB L2",
-                   "cold_plan_build_ms": cold_ms},
+                   "cold_plan_build_ms": cold_ms,
+                   "path": "fused" if fused_stats else "generic", "fused_plan": fused_stats},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": algo_bytes,
@@ -282,6 +291,10 @@ def main():
     ap.add_argument("--ref-cells", type=int, default=60, dest="ref_cells",
                     help="cells per side of the CPU sample (60 -> 1.3 M tets)")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--no-fused", action="store_true", dest="no_fused",
+                    help="time the generic two-kernel path instead of the fused P1 kernel")
+    ap.add_argument("--tile", type=int, default=1024)
+    ap.add_argument("--threads", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

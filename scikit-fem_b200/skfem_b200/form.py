@@ -44,7 +44,7 @@ def _torch():
     return torch
 
 
-_CONFIG = {"fused": True, "fused_tile": 1024}
+_CONFIG = {"fused": True, "fused_tile": 1024, "fused_threads": 256}
 
 
 def set_options(**kw):
@@ -410,7 +410,8 @@ class BilinearForm(Form):
                 fkey = ("fused", key)
                 fp = ubasis._plans.get(fkey)
                 if fp is None:
-                    fp = fused.build(ubasis, plan, T=fused_tile())
+                    fp = fused.build(ubasis, plan, T=fused_tile(),
+                                     threads=int(_CONFIG["fused_threads"]))
                     ubasis._plans[fkey] = fp
                 data = torch.empty(plan.nnz, dtype=torch.float64, device=fp.p.device)
                 fused.run(fp, data, _stream())

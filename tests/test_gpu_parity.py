@@ -185,14 +185,14 @@ def test_quadrature_mismatch_errors():
         laplace.assemble(b1, b2)
 
 
-@pytest.mark.parametrize("tile", [1024, 2048])
-def test_fused_p1_path(tile):
+@pytest.mark.parametrize("tile,threads", [(1024, 256), (1024, 512), (2048, 512), (512, 256)])
+def test_fused_p1_path(tile, threads):
     """Warm re-assembly goes through the fused kernel (csrc/skb_p1_fused.cu):
     same plan (indptr/indices bit-exact), values within rtol 1e-12 of the
     reference, bit-identical between repeated runs."""
     from skfem_b200.models.poisson import laplace
     from skfem_b200 import form as F
-    F.set_options(fused=True, fused_tile=tile)
+    F.set_options(fused=True, fused_tile=tile, fused_threads=threads)
     try:
         for name in ["tet_p1_tensor6", "tet_p1_ball2", "tet_p1_refined3", "tet_p1_morphed5",
                      "tet_p1_tensor_nonuniform"]:
@@ -232,4 +232,4 @@ def test_fused_p1_path(tile):
         np.testing.assert_allclose(As.data, Aso.data, rtol=RTOL,
                                    atol=RTOL * np.abs(Aso.data).max())
     finally:
-        F.set_options(fused=True, fused_tile=1024)
+        F.set_options(fused=True, fused_tile=1024, fused_threads=256)
