@@ -153,7 +153,8 @@ def run_gpu(args):
     from skfem_b200.models.poisson import laplace
 
     from skfem_b200 import form as _form
-    _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads)
+    _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads,
+                      fused_ring=args.ring)
     cells = args.cells
     x = np.linspace(0, 1, cells + 1)
     if world == 1:
@@ -172,9 +173,26 @@ def run_gpu(args):
     cold_ms = 1e3 * (time.perf_counter() - t0)
     nnz = A.nnz
 
-    def step():
-        return laplace.assemble_device(basis)
+    out = torch.empty(nnz, dtype=torch.float64, device="cuda")
 
+    def step_eager():
+        return laplace.assemble_device(basis, out=out)
+
+    for _ in range(2):
+        step_eager()                 # builds the fused tile plan on the first warm call
+    torch.cuda.synchronize()
+    launches_per_step = None
+    graph = None
+    if not args.no_graph:
+        # the warm step is launch bound from Python: capture it once, replay it
+        _lib.lib().skb_launch_count(1)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_eager()
+        launches_per_step = int(_lib.lib().skb_launch_count(1))
+        step = graph.replay
+    else:
+        step = step_eager
     for _ in range(max(args.warmup, 3)):
         step()
     if world > 1:
@@ -191,6 +209,8 @@ def run_gpu(args):
     ev1.record()
     torch.cuda.synchronize()
     launches = int(_lib.lib().skb_launch_count(0))
+    if graph is not None:            # replays launch the captured kernels, not the C API
+        launches = launches_per_step * args.steps
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -203,7 +223,7 @@ def run_gpu(args):
 
     # ---- end to end: host buffers in, scipy CSR out, through the public API ----
     e2e = None
-    if True:
+    if not args.no_e2e:
         p_pin = torch.from_numpy(m.p).pin_memory()
         t_pin = torch.from_numpy(m.t).pin_memory()
         p_host, t_host = p_pin.numpy(), t_pin.numpy()
@@ -246,7 +266,7 @@ def run_gpu(args):
         if isinstance(k, tuple) and k and k[0] == "fused":
             from skfem_b200 import fused as _fused
             fused_stats = _fused.stats(v)
-            fused_stats["tile"], fused_stats["threads"] = v.T, v.threads
+            fused_stats["tile"], fused_stats["threads"], fused_stats["ring"] = v.T, v.threads, v.ring
     algo_bytes = 4 * 4 * nel + 8 * 3 * nverts + 8 * nnz   # t + p + CSR data (warm)
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
     line = {
@@ -291,9 +311,13 @@ def main():
     ap.add_argument("--ref-cells", type=int, default=60, dest="ref_cells",
                     help="cells per side of the CPU sample (60 -> 1.3 M tets)")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    ap.add_argument("--no-graph", action="store_true", dest="no_graph",
+                    help="launch the warm step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-fused", action="store_true", dest="no_fused",
                     help="time the generic two-kernel path instead of the fused P1 kernel")
-    ap.add_argument("--tile", type=int, default=1024)
+    ap.add_argument("--tile", type=int, default=512)
+    ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--threads", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":

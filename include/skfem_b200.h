@@ -130,25 +130,28 @@ int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *se
  * BilinearForm._assemble (bilinear_form.py:58-128,150-151) and the value part of
  * COOData._assemble_scipy_csr (coo_data.py:27-36): local matrices are formed
  * in registers (bit-identical to numpy), staged in shared memory and reduced
- * per CSR slot inside the CTA; they never reach HBM.  The tile plan (tl,
- * tile_vert_start, tile_verts, tile_slot_start, tile_group_start,
- * tile_contrib_start, grp_base, grp_len, contrib, meta, sptr, gslot) is built
- * once per (mesh, pattern): see skfem_b200/fused.py for its layout.
- * (tile_elems, threads) must be one of (512,256) (512,512) (1024,256) (1024,512)
- * (1024,1024) (2048,512) (2048,1024); aux_bytes = shared bytes for the larger of
- * a tile's vertex coordinates (32 B each) and its index list (2 B each).
- * w = the common quadrature weight (all weights of the rule must be equal),
- * nqp = number of quadrature points.  skb_p1_combine adds, in tile order, the
- * per-tile partial sums of CSR slots touched by more than one tile.  No float
- * atomics: bit-reproducible.                                                 */
-int skb_p1tet_laplace_fused(const double *p, int64_t npts, const uint16_t *tl, int32_t ntiles,
-                            int32_t tile_elems, int32_t threads,
-                            const uint32_t *tile_vert_start, const int32_t *tile_verts,
-                            int32_t aux_bytes, const uint32_t *tile_slot_start,
-                            const uint32_t *tile_group_start, const uint32_t *tile_contrib_start,
-                            const uint32_t *grp_base, const uint16_t *grp_len,
-                            const uint16_t *contrib, const uint32_t *meta, double w, int32_t nqp,
-                            double *csr_data, double *scratch, void *stream);
+ * per CSR slot inside the CTA; they never reach HBM.  The plan is built once
+ * per (mesh, pattern) by skfem_b200/fused.py: elements are cut into tiles of
+ * tile_elems and every tile owns one contiguous record in `rec` (header, tile-
+ * local connectivity, vertex list, slot groups, slot targets, sliced-ELL
+ * contribution indices; layout documented in fused.py), rec_start[t] being its
+ * byte offset (multiple of 16).  The kernel is persistent and warp-specialised:
+ * tile_elems compute threads (one element each) + reduce_threads reduce
+ * threads per CTA; records stream through a ring of `ring` (4|5) shared
+ * buffers of rec_cap bytes by TMA bulk copies, vertex coordinates are gathered
+ * with cp.async; vcap = most vertices in a tile.  (tile_elems, reduce_threads)
+ * in {(256,128) (256,256) (512,128) (512,256) (512,512) (768,256)}.
+ * skb_p1_fused_smem_bytes gives the dynamic shared memory a configuration
+ * needs (must be <= 227 KB).  w = the common quadrature weight (all weights of
+ * the rule must be equal), nqp = number of quadrature points.  skb_p1_combine
+ * adds, in tile order, the per-tile partial sums of CSR slots touched by more
+ * than one tile.  No float atomics: bit-reproducible.                        */
+int64_t skb_p1_fused_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap, int32_t vcap);
+int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void *rec,
+                            const uint64_t *rec_start, int32_t ntiles, int32_t tile_elems,
+                            int32_t reduce_threads, int32_t ring, int32_t rec_cap, int32_t vcap,
+                            double w, int32_t nqp, double *csr_data, double *scratch,
+                            void *stream);
 int skb_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
                    int64_t nshared, double *csr_data, void *stream);
 

@@ -7,57 +7,52 @@
 //   COOData._assemble_scipy_csr  assembly/form/coo_data.py:27-36 (values)
 // for form = models/poisson.py:7-9 (laplace) on ElementTetP1.
 //
-// Data layout (built once per (mesh, pattern) by skfem_b200/fused.py):
-//   elements are ordered along a Morton curve and cut into tiles of T
-//   elements.  Per tile the plan holds the list of its distinct vertices, the
-//   connectivity rewritten in tile-local 16-bit vertex numbers and, for every
-//   CSR slot the tile touches ("tile slot"), the staging indices of the local
-//   entries that add into it.
-//   A CTA owns one tile at a time:
-//     phase 0  the tile's contribution-index list is requested into registers
-//              (consumed after phase 1, so its latency hides behind the FP64
-//              work) and the tile's vertex coordinates are gathered once into
-//              shared memory (3 loads per vertex instead of 12 per element);
-//     phase 1  every thread computes the 10 unique local entries of its
-//              elements in registers, bit-identical to numpy (Appendix A),
-//              and stages them in shared memory  vals[k*T + e];
-//     phase 2  the index list is parked in shared memory (over the dead
-//              coordinates) and one lane per tile slot adds that slot's staged
-//              contributions in a fixed order.  Slots are sorted by
-//              contribution count and stored sliced-ELL (groups of 32 slots,
-//              contribution k of lane l at base + 32k + l, short lists padded
-//              with the index of a staged 0.0) so lanes of a warp run equally
-//              long without predication.  The sum goes straight to csr_data
-//              (slot touched by this tile only) or to its reserved position in
-//              a scratch array grouped by CSR slot.
-//   skb_p1_combine then adds the per-tile partials of every shared slot in
-//   tile order.  No float atomics anywhere: results are bit-reproducible.
+// Plan (built once per (mesh, pattern) by skfem_b200/fused.py): elements are
+// ordered along a Morton curve and cut into tiles of T elements.  Each tile
+// owns one contiguous, 16-byte aligned *record* in HBM:
+//     header | tl: T x ushort4 tile-local vertex ids | verts: global vertex ids
+//     | grp: per 32-slot group {offset/32, length} | meta: per tile slot the CSR
+//     slot or (bit 31) the scratch position | ids: sliced-ELL staging indices
+//
+// Kernel: persistent CTAs, software pipeline over the CTA's tiles
+//   TMA   the record of tile k+NR-1 is fetched by one cp.async.bulk (UBLKCP)
+//         into a ring of NR shared buffers, completion on an mbarrier;
+//   LDGSTS the vertex coordinates of tile k+1 are gathered asynchronously
+//         (cp.async, 3 x 8 B per vertex) into a double-buffered coordinate
+//         array as soon as its record has landed;
+//   P1    every thread forms the 10 unique local entries of its element(s) in
+//         registers, bit-identical to numpy (no FMA
+//         contraction, reference operation order, correctly rounded division)
+//         and stages them  vals[k*T + e];
+//   P2    one lane per tile slot adds that slot's staged contributions in a
+//         fixed order (sliced ELL: contribution k of lane l at base + 32k + l,
+//         short lists padded with the index of a staged 0.0) and writes the
+//         sum to csr_data (slot touched by this tile only) or to its reserved
+//         position in a scratch array grouped by CSR slot.
+// skb_p1_combine then adds the per-tile partials of every shared slot in tile
+// order.  No float atomics anywhere: results are bit-reproducible.
 #include "skb_common.cuh"
 
 namespace skb {
 
-struct P1Plan {
+struct P1Args {
   const double *p;
   int64_t npts;
-  const ushort4 *tl;                 // [ntiles*T] tile-local vertex ids, 0xFFFF = padding
-  int32_t ntiles, T;
-  const uint32_t *tile_vert_start;   // [ntiles+1]
-  const int32_t *tile_verts;         // global vertex ids of each tile
-  const uint32_t *tile_slot_start;   // [ntiles+1] first tile slot of each tile
-  const uint32_t *tile_group_start;  // [ntiles+1] first 32-slot group of each tile
-  const uint32_t *tile_contrib_start;// [ntiles+1] first index of each tile, multiples of 8
-  const uint32_t *grp_base;          // per group: tile-relative offset into contrib
-  const uint16_t *grp_len;           // per group: (padded) contribution list length
-  const uint16_t *contrib;           // sliced-ELL staging indices k*T + e, 10*T = "zero"
-  const uint32_t *meta;              // per tile slot: bit31 ? scratch position : csr slot
+  const unsigned char *rec;     // concatenated tile records
+  const uint64_t *rec_start;    // [ntiles+1] byte offsets (multiples of 16)
+  int32_t ntiles;
+  int32_t rec_cap;              // largest record, bytes (multiple of 16)
+  int32_t vcap;                 // most vertices in one tile
   double *csr_data;
   double *scratch;
-  double w;                          // the common quadrature weight
+  double w;                     // the common quadrature weight
   int32_t nqp;
-  int32_t aux_bytes;                 // shared bytes for coordinates / index list
 };
 
-// unique (a<=b) local entries: k index of pair (a,b), 4 basis functions
+struct RecHeader {              // 32 bytes at the start of every record
+  uint32_t nverts, ngroups, off_verts, off_grp, off_meta, off_ids, nslots, bytes;
+};
+
 __device__ __forceinline__ constexpr int sym_index4(int a, int b) {  // a <= b
   return a * 4 - (a * (a - 1)) / 2 + (b - a);
 }
@@ -81,142 +76,257 @@ __device__ __forceinline__ double sum_equal_terms(double v, int nqp) {
 
 // |c| is 0 or within [2^-60, 2^60]: if every coordinate of a tile passes, all
 // cofactors are 0 or in [2^-278, 2^123] and a nonzero determinant lies in
-// [2^-391, 2^184], so exact_div() can neither overflow nor underflow and the
-// per-element exponent checks of divide9() are unnecessary.
+// [2^-443, 2^186], so exact_div() can neither overflow nor underflow and no
+// per-element exponent checks are needed ("exact division").
 __device__ __forceinline__ bool coord_tame(double c) {
   const unsigned h = (unsigned)__double2hiint(c) & 0x7fffffffu;
   const bool zero = (h | (unsigned)__double2loint(c)) == 0u;
   return zero | ((h - 0x3c300000u) <= (0x43b00000u - 0x3c300000u));
 }
 
-constexpr int P1_MAX_PREFETCH = 4;  // uint4 (8 indices) per thread
+// ---- async-copy / mbarrier primitives (PTX) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
-template <int T_ELEMS, int THREADS, bool NQP4>
-__global__ void __launch_bounds__(THREADS)
-p1tet_laplace_fused_kernel(const P1Plan pl) {
-  extern __shared__ double smem[];
-  double *vals = smem;                                 // [10*T + 2], [10*T] == 0.0
-  double4 *sxyz = reinterpret_cast<double4 *>(smem + 10 * T_ELEMS + 2);  // coordinates (32 B)
-  uint4 *sidx4 = reinterpret_cast<uint4 *>(sxyz);      // later: the index list
-  const uint16_t *sidx = reinterpret_cast<const uint16_t *>(sxyz);
-  __shared__ int s_wild;
-  constexpr int PER_THREAD = T_ELEMS / THREADS;
-  constexpr int NWARPS = THREADS / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { vals[10 * T_ELEMS] = 0.0; s_wild = 0; }
+// Warp-specialised persistent kernel.  A CTA = T "compute" threads (one
+// element each, FP64 bound) + NRED "reduce" threads (shared-memory latency
+// bound).  In iteration k the compute warps run P1 of tile k into vals[k&1]
+// while the reduce warps run P2 of tile k-1 out of vals[(k-1)&1], request the
+// vertex gather of tile k+2 and retire the gather of tile k+1; one block
+// barrier per iteration, then one thread re-arms the freed record buffer with
+// the TMA fetch of tile k-1+NR.
+template <int T_ELEMS, int NRED, int NR, bool NQP4>
+__global__ void __launch_bounds__(T_ELEMS + NRED)
+p1tet_laplace_fused_kernel(const P1Args a) {
+  static_assert(NR >= 4, "record ring must hold tiles k-1 .. k+2");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int VSTRIDE = 10 * T_ELEMS + 2;
+  // shared layout: vals[2] | coords[3] | records[NR] | mbarriers | flags | counters
+  double *vals = reinterpret_cast<double *>(smem_raw);                      // [2][VSTRIDE]
+  double4 *coords = reinterpret_cast<double4 *>(vals + 2 * VSTRIDE);        // [3][vcap]
+  unsigned char *recs = reinterpret_cast<unsigned char *>(coords + 3 * a.vcap);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(recs + (size_t)NR * a.rec_cap);
+  int *s_wild = reinterpret_cast<int *>(mbar + NR);                         // [3]
+  int *s_next = s_wild + 3;                                                 // [2]
+  const bool is_compute = threadIdx.x < T_ELEMS;
+  const int rtid = (int)threadIdx.x - T_ELEMS;        // reduce-thread index
+  const int lane = threadIdx.x & 31;
+  const int nk = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+  auto rec_of = [&](int k) { return recs + (size_t)(k % NR) * a.rec_cap; };
+  auto issue = [&](int k) {   // one thread: fetch the record of this CTA's k-th tile
+    if (k < nk) {
+      const int t = tile_of(k);
+      const uint64_t b0 = a.rec_start[t];
+      const unsigned bytes = (unsigned)(a.rec_start[t + 1] - b0);
+      fence_proxy_async();
+      mbar_expect_tx(&mbar[k % NR], bytes);
+      tma_bulk_g2s(rec_of(k), a.rec + b0, bytes, &mbar[k % NR]);
+    }
+  };
+  auto wait_rec = [&](int k) { mbar_wait(&mbar[k % NR], (unsigned)((k / NR) & 1)); };
+  auto gather = [&](int k) {  // reduce threads: async gather of tile k's vertex coordinates
+    const unsigned char *r = rec_of(k);
+    const RecHeader *h = reinterpret_cast<const RecHeader *>(r);
+    const int nv = (int)h->nverts;
+    const int32_t *verts = reinterpret_cast<const int32_t *>(r + h->off_verts);
+    double4 *dst = coords + (size_t)(k % 3) * a.vcap;
+    const double *px = a.p, *py = a.p + a.npts, *pz = a.p + 2 * a.npts;
+    for (int i = rtid; i < nv; i += NRED) {
+      const int32_t gv = verts[i];
+      cp_async8(&dst[i].x, px + gv);
+      cp_async8(&dst[i].y, py + gv);
+      cp_async8(&dst[i].z, pz + gv);
+    }
+  };
+  auto check_tame = [&](int k) {  // reduce threads, after their copies of tile k landed
+    const RecHeader *h = reinterpret_cast<const RecHeader *>(rec_of(k));
+    const int nv = (int)h->nverts;
+    const double4 *src = coords + (size_t)(k % 3) * a.vcap;
+    bool wild = false;
+    for (int i = rtid; i < nv; i += NRED) {
+      const double4 c = src[i];
+      wild |= !(coord_tame(c.x) & coord_tame(c.y) & coord_tame(c.z));
+    }
+    if (wild) s_wild[k % 3] = 1;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NR; ++i) mbar_init(&mbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    vals[10 * T_ELEMS] = 0.0;
+    vals[VSTRIDE + 10 * T_ELEMS] = 0.0;
+    s_wild[0] = s_wild[1] = s_wild[2] = 0;
+    s_next[0] = s_next[1] = 0;
+  }
   __syncthreads();
-  for (int tile = blockIdx.x; tile < pl.ntiles; tile += gridDim.x) {
-    // ---- phase 0: request the index list, stage vertex coordinates -------------
-    const uint32_t c0 = pl.tile_contrib_start[tile], c1 = pl.tile_contrib_start[tile + 1];
-    const int nvec = (int)((c1 - c0) >> 3);
-    uint4 pf[P1_MAX_PREFETCH];
-    {
-      const uint4 *src = reinterpret_cast<const uint4 *>(pl.contrib + c0);
+  if (nk <= 0) return;
+  // prologue: records 0..NR-2 in flight, coordinates of tiles 0 and 1 resident
+  if (threadIdx.x == 0)
+    for (int k = 0; k < NR; ++k) issue(k);
+  if (!is_compute) {
+    wait_rec(0);
+    gather(0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (nk > 1) { wait_rec(1); gather(1); }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    cp_async_wait_all();
+    check_tame(0);
+    if (nk > 1) check_tame(1);
+  }
+  __syncthreads();
+
+  for (int k = 0; k <= nk; ++k) {
+    if (is_compute) {
+      // ---- P1(k): local matrices of tile k -> vals[k & 1] ---------------------------
+      if (k < nk) {
+        wait_rec(k);
+        const unsigned char *r = rec_of(k);
+        const bool tame = (s_wild[k % 3] == 0);
+        const ushort4 *tl = reinterpret_cast<const ushort4 *>(r + sizeof(RecHeader));
+        const double4 *xyz = coords + (size_t)(k % 3) * a.vcap;
+        double *out = vals + (size_t)(k & 1) * VSTRIDE;
+        const int el = threadIdx.x;
+        const ushort4 v = tl[el];
+        if (v.x != 0xFFFF) {  // not a padding element of the last tile
+          double A[3][3];
+          {
+            const double4 q0 = xyz[v.x], q1 = xyz[v.y], q2 = xyz[v.z], q3 = xyz[v.w];
+            A[0][0] = q1.x - q0.x; A[0][1] = q2.x - q0.x; A[0][2] = q3.x - q0.x;
+            A[1][0] = q1.y - q0.y; A[1][1] = q2.y - q0.y; A[1][2] = q3.y - q0.y;
+            A[2][0] = q1.z - q0.z; A[2][1] = q2.z - q0.z; A[2][2] = q3.z - q0.z;
+          }
+          const double det = det3(A);
+          double n[3][3], inv[3][3];
+          cofactors3(A, n);
+          if (tame && det != 0.0) {
+            const double y = __drcp_rn(det);
 #pragma unroll
-      for (int r = 0; r < P1_MAX_PREFETCH; ++r) {
-        const int i = r * THREADS + threadIdx.x;
-        if (i < nvec) pf[r] = __ldg(src + i);
-      }
-    }
-    {
-      const uint32_t v0 = pl.tile_vert_start[tile], v1 = pl.tile_vert_start[tile + 1];
-      const double *px = pl.p, *py = pl.p + pl.npts, *pz = pl.p + 2 * pl.npts;
-      bool wild = false;
-      for (int i = threadIdx.x; i < (int)(v1 - v0); i += THREADS) {
-        const int32_t gv = __ldg(pl.tile_verts + v0 + i);
-        const double x = __ldg(px + gv), y = __ldg(py + gv), z = __ldg(pz + gv);
-        wild |= !(coord_tame(x) & coord_tame(y) & coord_tame(z));
-        sxyz[i] = make_double4(x, y, z, 0.0);
-      }
-      if (wild) s_wild = 1;
-    }
-    __syncthreads();
-    const bool tame = (s_wild == 0);
-    // ---- phase 1: local matrices -------------------------------------------------
-#pragma unroll 1
-    for (int it = 0; it < PER_THREAD; ++it) {
-      const int el = it * THREADS + threadIdx.x;
-      const ushort4 v = __ldg(pl.tl + (int64_t)tile * T_ELEMS + el);
-      if (v.x == 0xFFFF) continue;  // padding of the last tile
-      double A[3][3];
-      {
-        const double4 q0 = sxyz[v.x], q1 = sxyz[v.y], q2 = sxyz[v.z], q3 = sxyz[v.w];
-        A[0][0] = q1.x - q0.x; A[0][1] = q2.x - q0.x; A[0][2] = q3.x - q0.x;
-        A[1][0] = q1.y - q0.y; A[1][1] = q2.y - q0.y; A[1][2] = q3.y - q0.y;
-        A[2][0] = q1.z - q0.z; A[2][1] = q2.z - q0.z; A[2][2] = q3.z - q0.z;
-      }
-      const double det = det3(A);
-      double n[3][3], inv[3][3];
-      cofactors3(A, n);
-      if (tame && det != 0.0) {
-        const double y = __drcp_rn(det);
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+              for (int j = 0; j < 3; ++j) inv[i][j] = exact_div(n[i][j], det, y);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) inv[i][j] = exact_div(n[i][j], det, y);
-      } else {
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+              for (int j = 0; j < 3; ++j) inv[i][j] = n[i][j] / det;
+          }
+          // P1 push-forward: dphi_b is +-unit, so grad_b (b=1..3) is row b-1 of
+          // inv and grad_0[j] = -((inv0j + inv1j) + inv2j)   (Appendix A.4)
+          double g[4][3];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) inv[i][j] = n[i][j] / det;
-      }
-      // P1 push-forward: dphi_b is +-unit, so grad_b (b=1..3) is row b-1 of inv
-      // and grad_0[j] = -((inv0j + inv1j) + inv2j)   (Appendix A.4)
-      double g[4][3];
+          for (int j = 0; j < 3; ++j) {
+            g[0][j] = -((inv[0][j] + inv[1][j]) + inv[2][j]);
+            g[1][j] = inv[0][j];
+            g[2][j] = inv[1][j];
+            g[3][j] = inv[2][j];
+          }
+          const double dx = fabs(det) * a.w;  // cell_basis.py:104-105
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        g[0][j] = -((inv[0][j] + inv[1][j]) + inv[2][j]);
-        g[1][j] = inv[0][j];
-        g[2][j] = inv[1][j];
-        g[3][j] = inv[2][j];
-      }
-      const double dx = fabs(det) * pl.w;  // cell_basis.py:104-105
+          for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = a; b < 4; ++b) {
-          const double d = (g[a][0] * g[b][0] + g[a][1] * g[b][1]) + g[a][2] * g[b][2];
-          vals[sym_index4(a, b) * T_ELEMS + el] = sum_equal_terms<NQP4>(d * dx, pl.nqp);
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: park the index list, then per-slot sums in fixed order ---------
-#pragma unroll
-    for (int r = 0; r < P1_MAX_PREFETCH; ++r) {
-      const int i = r * THREADS + threadIdx.x;
-      if (i < nvec) sidx4[i] = pf[r];
-    }
-    for (int i = P1_MAX_PREFETCH * THREADS + threadIdx.x; i < nvec; i += THREADS)
-      sidx4[i] = __ldg(reinterpret_cast<const uint4 *>(pl.contrib + c0) + i);
-    __syncthreads();
-    {
-      const uint32_t s0 = pl.tile_slot_start[tile];
-      const int nslots = (int)(pl.tile_slot_start[tile + 1] - s0);
-      const uint32_t g0 = pl.tile_group_start[tile], g1 = pl.tile_group_start[tile + 1];
-      for (uint32_t g = g0 + warp; g < g1; g += NWARPS) {
-        const int j = (int)(g - g0) * 32 + lane;
-        const int len = (int)__ldg(pl.grp_len + g);
-        const uint16_t *cb = sidx + __ldg(pl.grp_base + g) + lane;
-        const uint32_t m = (j < nslots) ? __ldg(pl.meta + s0 + j) : 0xffffffffu;
-        double acc = 0.0;
-        int k = 0;
-        for (; k + 4 <= len; k += 4) {
-          const int i0 = cb[k * 32], i1 = cb[(k + 1) * 32], i2 = cb[(k + 2) * 32],
-                    i3 = cb[(k + 3) * 32];
-          const double a0 = vals[i0], a1 = vals[i1], a2 = vals[i2], a3 = vals[i3];
-          acc = acc + a0;
-          acc = acc + a1;
-          acc = acc + a2;
-          acc = acc + a3;
-        }
-        for (; k < len; ++k) acc = acc + vals[cb[k * 32]];
-        if (m != 0xffffffffu) {
-          if (m & 0x80000000u) pl.scratch[m & 0x7fffffffu] = acc;
-          else pl.csr_data[m] = acc;
+            for (int q = p; q < 4; ++q) {
+              const double d = (g[p][0] * g[q][0] + g[p][1] * g[q][1]) + g[p][2] * g[q][2];
+              out[sym_index4(p, q) * T_ELEMS + el] = sum_equal_terms<NQP4>(d * dx, a.nqp);
+            }
         }
       }
+    } else {
+      // ---- reduce warps -----------------------------------------------------------------
+      if (rtid == 0) {
+        s_next[(k + 1) & 1] = 0;      // counter of the next iteration's P2
+        s_wild[(k + 2) % 3] = 0;      // flag of tile k+2 (last read for tile k-1)
+      }
+      if (k >= 1) {
+        // ---- P2(k-1): per-slot sums in fixed order (sliced ELL, in shared memory) -----
+        const unsigned char *r = rec_of(k - 1);
+        const RecHeader *h = reinterpret_cast<const RecHeader *>(r);
+        const double *in = vals + (size_t)((k - 1) & 1) * VSTRIDE;
+        const int ngroups = (int)h->ngroups;
+        const uint32_t *grp = reinterpret_cast<const uint32_t *>(r + h->off_grp);
+        const uint32_t *meta = reinterpret_cast<const uint32_t *>(r + h->off_meta);
+        const uint16_t *ids = reinterpret_cast<const uint16_t *>(r + h->off_ids);
+        int *counter = &s_next[k & 1];
+        for (;;) {  // groups are sorted longest first: dynamic hand-out balances the warps
+          int g = 0;
+          if (lane == 0) g = atomicAdd(counter, 1);
+          g = __shfl_sync(0xffffffffu, g, 0);
+          if (g >= ngroups) break;
+          const uint32_t gi = grp[g];
+          const int len = (int)(gi >> 16);
+          const uint16_t *cb = ids + (size_t)(gi & 0xffffu) * 32 + lane;
+          const uint32_t m = meta[g * 32 + lane];
+          double acc = 0.0;
+          int c = 0;
+          for (; c + 4 <= len; c += 4) {
+            const int i0 = cb[c * 32], i1 = cb[(c + 1) * 32], i2 = cb[(c + 2) * 32],
+                      i3 = cb[(c + 3) * 32];
+            const double a0 = in[i0], a1 = in[i1], a2 = in[i2], a3 = in[i3];
+            acc = acc + a0;
+            acc = acc + a1;
+            acc = acc + a2;
+            acc = acc + a3;
+          }
+          for (; c < len; ++c) acc = acc + in[cb[c * 32]];
+          if (m != 0xffffffffu) {
+            if (m & 0x80000000u) a.scratch[m & 0x7fffffffu] = acc;
+            else a.csr_data[m] = acc;
+          }
+        }
+      }
+      // request the vertex gather of tile k+2 (its record has been in flight
+      // for at least P2's duration), retire the gather of tile k+1 (requested
+      // one iteration ago)
+      if (k + 2 < nk) {
+        wait_rec(k + 2);
+        gather(k + 2);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      if (k >= 1 && k + 1 < nk) check_tame(k + 1);
     }
-    __syncthreads();
+    __syncthreads();  // vals[k&1] complete; record k-1 free; coords of tile k+1 visible
+    if (threadIdx.x == 0 && k >= 1) issue(k - 1 + NR);  // into the buffer tile k-1 vacated
   }
 }
 
@@ -233,68 +343,63 @@ p1_combine_kernel(const double *__restrict__ scratch, const uint32_t *__restrict
   }
 }
 
+template <int TT, int NRED, int NR>
+static int launch_fused(const P1Args &a, size_t smem, int sms, bool q4, cudaStream_t st) {
+  const int grid = a.ntiles < sms ? a.ntiles : sms;
+  if (q4) {
+    auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, true>;
+    SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, TT + NRED, smem, st>>>(a);
+  } else {
+    auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, false>;
+    SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, TT + NRED, smem, st>>>(a);
+  }
+  return (int)cudaGetLastError();
+}
+
 }  // namespace skb
 
-extern "C" int skb_p1tet_laplace_fused(const double *p, int64_t npts, const uint16_t *tl,
-                                       int32_t ntiles, int32_t tile_elems, int32_t threads,
-                                       const uint32_t *tile_vert_start, const int32_t *tile_verts,
-                                       int32_t aux_bytes, const uint32_t *tile_slot_start,
-                                       const uint32_t *tile_group_start,
-                                       const uint32_t *tile_contrib_start,
-                                       const uint32_t *grp_base, const uint16_t *grp_len,
-                                       const uint16_t *contrib, const uint32_t *meta, double w,
-                                       int32_t nqp, double *csr_data, double *scratch,
-                                       void *stream) {
+extern "C" int64_t skb_p1_fused_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap,
+                                           int32_t vcap) {
+  return (int64_t)(sizeof(double) * 2 * (10 * (size_t)tile_elems + 2) + 3 * (size_t)vcap * 32 +
+                   (size_t)ring * rec_cap + 8 * (size_t)ring + 32);
+}
+
+extern "C" int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void *rec,
+                                       const uint64_t *rec_start, int32_t ntiles,
+                                       int32_t tile_elems, int32_t reduce_threads, int32_t ring,
+                                       int32_t rec_cap, int32_t vcap, double w, int32_t nqp,
+                                       double *csr_data, double *scratch, void *stream) {
   using namespace skb;
-  if (ntiles < 0 || !p || nqp <= 0 || aux_bytes <= 0) return SKB_EINVAL;
+  if (ntiles < 0 || !p || nqp <= 0 || vcap <= 0 || rec_cap <= 0 || (rec_cap & 15)) return SKB_EINVAL;
   if (ntiles == 0) return SKB_OK;
-  P1Plan pl;
-  pl.p = p; pl.npts = npts; pl.tl = (const ushort4 *)tl; pl.ntiles = ntiles; pl.T = tile_elems;
-  pl.tile_vert_start = tile_vert_start; pl.tile_verts = tile_verts;
-  pl.tile_slot_start = tile_slot_start; pl.tile_group_start = tile_group_start;
-  pl.tile_contrib_start = tile_contrib_start;
-  pl.grp_base = grp_base; pl.grp_len = grp_len; pl.contrib = contrib; pl.meta = meta;
-  pl.csr_data = csr_data; pl.scratch = scratch; pl.w = w; pl.nqp = nqp;
-  pl.aux_bytes = aux_bytes;
+  P1Args a;
+  a.p = p; a.npts = npts; a.rec = (const unsigned char *)rec; a.rec_start = rec_start;
+  a.ntiles = ntiles; a.rec_cap = rec_cap; a.vcap = vcap;
+  a.csr_data = csr_data; a.scratch = scratch; a.w = w; a.nqp = nqp;
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = sizeof(double) * (10 * (size_t)tile_elems + 2) + (size_t)aux_bytes;
-  if (smem > 226 * 1024) return SKB_ETOOBIG;
-  int per_sm = (int)((227 * 1024) / (smem + 1024 + 16));
-  if (per_sm * threads > 2048) per_sm = 2048 / threads;
-  if (per_sm < 1) per_sm = 1;
-#define SKB_P1_LAUNCH(TT, TH, Q4)                                                             \
-  do {                                                                                        \
-    auto k = p1tet_laplace_fused_kernel<TT, TH, Q4>;                                          \
-    SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                      (int)smem));                                            \
-    const int cap = per_sm * sms;                                                             \
-    const int grid = ntiles < cap ? ntiles : cap;                                             \
-    k<<<grid, TH, smem, st>>>(pl);                                                            \
-  } while (0)
+  const size_t smem = (size_t)skb_p1_fused_smem_bytes(tile_elems, ring, rec_cap, vcap);
+  if (smem > 227 * 1024) return SKB_ETOOBIG;
   const bool q4 = (nqp == 4);
-  if (tile_elems == 1024 && threads == 256) {
-    if (q4) SKB_P1_LAUNCH(1024, 256, true); else SKB_P1_LAUNCH(1024, 256, false);
-  } else if (tile_elems == 1024 && threads == 512) {
-    if (q4) SKB_P1_LAUNCH(1024, 512, true); else SKB_P1_LAUNCH(1024, 512, false);
-  } else if (tile_elems == 1024 && threads == 1024) {
-    if (q4) SKB_P1_LAUNCH(1024, 1024, true); else SKB_P1_LAUNCH(1024, 1024, false);
-  } else if (tile_elems == 2048 && threads == 512) {
-    if (q4) SKB_P1_LAUNCH(2048, 512, true); else SKB_P1_LAUNCH(2048, 512, false);
-  } else if (tile_elems == 2048 && threads == 1024) {
-    if (q4) SKB_P1_LAUNCH(2048, 1024, true); else SKB_P1_LAUNCH(2048, 1024, false);
-  } else if (tile_elems == 512 && threads == 256) {
-    if (q4) SKB_P1_LAUNCH(512, 256, true); else SKB_P1_LAUNCH(512, 256, false);
-  } else if (tile_elems == 512 && threads == 512) {
-    if (q4) SKB_P1_LAUNCH(512, 512, true); else SKB_P1_LAUNCH(512, 512, false);
-  } else {
-    return SKB_EINVAL;
+  int rc = SKB_EINVAL;
+#define SKB_P1_CASE(TT, NRED)                                                  \
+  if (tile_elems == TT && reduce_threads == NRED) {                            \
+    if (ring == 4) rc = launch_fused<TT, NRED, 4>(a, smem, sms, q4, st);       \
+    else if (ring == 5) rc = launch_fused<TT, NRED, 5>(a, smem, sms, q4, st);  \
   }
-#undef SKB_P1_LAUNCH
-  count_launch();
-  return (int)cudaGetLastError();
+  SKB_P1_CASE(256, 128)
+  SKB_P1_CASE(256, 256)
+  SKB_P1_CASE(512, 128)
+  SKB_P1_CASE(512, 256)
+  SKB_P1_CASE(512, 512)
+  SKB_P1_CASE(768, 256)
+#undef SKB_P1_CASE
+  if (rc == SKB_OK) count_launch();
+  return rc;
 }
 
 extern "C" int skb_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,

@@ -44,7 +44,7 @@ def _torch():
     return torch
 
 
-_CONFIG = {"fused": True, "fused_tile": 1024, "fused_threads": 256}
+_CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 256, "fused_ring": 4}
 
 
 def set_options(**kw):
@@ -393,8 +393,13 @@ class BilinearForm(Form):
         return (id(self.form) if self.native is None else self.native[:3],
                 id(vbasis) if vbasis is not None else None)
 
-    def assemble_device(self, ubasis, vbasis=None, **kwargs) -> DeviceCSR:
-        """Assemble into a device-resident CSR (no host transfer)."""
+    def assemble_device(self, ubasis, vbasis=None, out=None, **kwargs) -> DeviceCSR:
+        """Assemble into a device-resident CSR (no host transfer).
+
+        ``out``: optional float64 device tensor of length nnz that receives
+        the values (warm calls only - the plan must exist).  With ``out`` the
+        call allocates nothing and can be captured in a CUDA graph, which is
+        how re-assembly loops (time stepping, Newton) should drive it."""
         assert self.form is not None
         torch = _torch()
         vb = ubasis if vbasis is None else vbasis
@@ -408,21 +413,27 @@ class BilinearForm(Form):
             from . import fused
             if fused.applicable(ubasis, self):
                 fkey = ("fused", key)
-                fp = ubasis._plans.get(fkey)
-                if fp is None:
-                    fp = fused.build(ubasis, plan, T=fused_tile(),
-                                     threads=int(_CONFIG["fused_threads"]))
-                    ubasis._plans[fkey] = fp
-                data = torch.empty(plan.nnz, dtype=torch.float64, device=fp.p.device)
-                fused.run(fp, data, _stream())
-                return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
+                fp = ubasis._plans.get(fkey, False)
+                if fp is False:
+                    fp = fused.build_auto(ubasis, plan, T=fused_tile(),
+                                          threads=int(_CONFIG["fused_threads"]),
+                                          ring=int(_CONFIG["fused_ring"]))
+                    ubasis._plans[fkey] = fp      # None: tiles too big, stay generic
+                if fp is not None:
+                    data = out if out is not None else torch.empty(
+                        plan.nnz, dtype=torch.float64, device=fp.p.device)
+                    fused.run(fp, data, _stream())
+                    return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
         local = self._local(ubasis, vbasis, **kwargs)
         if plan is None:
+            if out is not None:
+                raise ValueError("out= needs an existing plan: assemble once without it")
             plan = build_plan(vb._dev()["edofs"], ubasis._dev()["edofs"], ubasis.nelems,
                               (vb.N, ubasis.N), local, drop_zeros=True)
             if key is not None:
                 ubasis._plans[key] = plan
-        data = torch.empty(plan.nnz, dtype=torch.float64, device=local.device)
+        data = out if out is not None else torch.empty(plan.nnz, dtype=torch.float64,
+                                                       device=local.device)
         code = _lib.lib().skb_csr_reduce(local.data_ptr(), plan.perm.data_ptr(),
                                          plan.segptr.data_ptr(), plan.nnz, data.data_ptr(),
                                          _stream())

@@ -3,19 +3,28 @@
 Built once per (basis, CSR pattern) on the device, reused by every warm
 re-assembly.  Input: the connectivity ``t``, the vertex coordinates (only to
 order elements along a Morton curve - any order is valid, a spatially compact
-one keeps tiles' slot sets small) and the CSR pattern ``indptr/indices``
+one keeps the tiles' slot sets small) and the CSR pattern ``indptr/indices``
 produced by the generic plan (skb_plan_*), which already encodes the
 value-dependent zero elimination of the reference
 (skfem/assembly/form/coo_data.py:35).
 
-Output (all device arrays):
-  tt                 (ntiles*T, 4) int32   tile-ordered connectivity, -1 padded
-  tile_slot_start    (ntiles+1,)  first tile slot of each tile
-  tile_contrib_start (ntiles+1,)  first contributor of each tile
-  slot_ptr           per tile (nslots+1) uint16 offsets into its contributors
-  contrib            uint16 staging indices  k(a,b)*T + e_local
-  meta               per tile slot: CSR slot, or 0x80000000|scratch position
-  sptr, gslot        per shared CSR slot: its scratch range and CSR slot
+Elements are cut into tiles of ``T``.  Every tile gets one contiguous,
+16-byte aligned *record* (fetched by a single TMA bulk copy in the kernel):
+
+    header  8 x uint32: nverts, ngroups, off_verts, off_grp, off_meta, off_ids,
+            nslots, bytes
+    tl      T x 4 uint16  tile-local vertex ids (0xFFFF = padding element)
+    verts   nverts int32  global vertex ids of the tile
+    grp     per group of 32 tile slots: uint32 (offset/32 into ids) | len << 16
+    meta    per tile slot: CSR slot, or 0x80000000 | scratch position
+            (0xFFFFFFFF for the unused lanes of the last group)
+    ids     sliced-ELL uint16 staging indices k(a,b)*T + e_local; entry c of
+            lane l of a group sits at base + 32 c + l; short lists are padded
+            with 10*T, the index of a staged 0.0
+
+A *tile slot* is a CSR slot touched by the tile.  Slots touched by one tile
+only are written straight to ``csr_data``; the others go to ``scratch``
+(grouped by CSR slot, tiles ascending) and are added by ``skb_p1_combine``.
 
 The preprocessing itself uses torch sort / unique / searchsorted (cold path,
 plumbing); the warm path runs only this package's kernels.
@@ -58,7 +67,7 @@ def applicable(basis, form):
     return bool(np.all(W == W[0]))
 
 
-def build(basis, plan, T=1024, threads=256):
+def build(basis, plan, T=512, threads=256, ring=2):
     torch = _torch()
     d = basis._dev()
     dev = d["device"]
@@ -68,10 +77,17 @@ def build(basis, plan, T=1024, threads=256):
     nnz = plan.nnz
     N = int(plan.shape[1])
     fp = P1FusedPlan()
-    fp.T, fp.threads, fp.nel, fp.nnz = T, threads, nel, nnz
+    fp.T, fp.threads, fp.ring, fp.nel, fp.nnz = T, threads, ring, nel, nnz
     ntiles = (nel + T - 1) // T
     fp.ntiles = ntiles
     i64 = torch.int64
+
+    def arange(n):
+        return torch.arange(n, device=dev, dtype=i64)
+
+    def excl(x):
+        return torch.cumsum(x, 0) - x
+
     tl = t.long()
     # 1. Morton order of element centroids
     cent = p[:, tl].sum(dim=1)                      # (3, nel), 4x centroid
@@ -82,30 +98,28 @@ def build(basis, plan, T=1024, threads=256):
     order = torch.argsort(code, stable=True)
     del cent, q, code
     tt = tl[:, order].t().contiguous()              # (nel, 4) int64, tile order
-    e_idx = torch.arange(nel, device=dev, dtype=i64)
+    e_idx = arange(nel)
     tile_of = e_idx // T
     e_loc = e_idx - tile_of * T
-    tile_ids = torch.arange(ntiles + 1, device=dev, dtype=i64)
+    tile_ids = arange(ntiles + 1)
     # 2. tile-local vertex numbering
     nv = int(p.shape[1])
     vkey = (tile_of[:, None] * nv + tt).reshape(-1)
     uv, vinv = torch.unique(vkey, sorted=True, return_inverse=True)
     uv_tile = uv // nv
     tile_vert_start = torch.searchsorted(uv_tile, tile_ids)
-    fp.vcap = int((tile_vert_start[1:] - tile_vert_start[:-1]).max())
-    if fp.vcap > 0xFFFF - 1:
+    nverts_tile = tile_vert_start[1:] - tile_vert_start[:-1]
+    fp.vcap = int(nverts_tile.max())
+    if fp.vcap >= 0xFFFF:
         raise RuntimeError("fused plan: tile touches too many vertices")
     loc = (vinv - tile_vert_start[tile_of].repeat_interleave(4)).reshape(nel, 4)
-    pad = ntiles * T - nel
-    if pad:
-        loc = torch.cat([loc, torch.full((pad, 4), 0xFFFF, dtype=i64, device=dev)])
-    fp.tl = loc.to(torch.int16).contiguous()
-    fp.tile_verts = (uv - uv_tile * nv).to(torch.int32).contiguous()
-    fp.tile_vert_start = tile_vert_start.to(torch.int32).contiguous()
-    del vkey, uv, vinv, loc, uv_tile
+    vert_gid = uv - uv_tile * nv
+    vert_tile = uv_tile
+    vert_loc = arange(int(uv.shape[0])) - tile_vert_start[uv_tile]
+    del vkey, uv, vinv
     # 3. CSR slot of every local entry (a, b)
     counts = (plan.indptr[1:] - plan.indptr[:-1]).long()
-    row_of_slot = torch.repeat_interleave(torch.arange(N, device=dev, dtype=i64), counts)
+    row_of_slot = torch.repeat_interleave(arange(N), counts)
     csr_key = row_of_slot * N + plan.indices.long()  # ascending (canonical CSR)
     del row_of_slot
     keys2, sids = [], []
@@ -129,16 +143,15 @@ def build(basis, plan, T=1024, threads=256):
     del key2
     nts = int(uniq.shape[0])
     ncontrib = int(sid.shape[0])
-    if int(cnt.max()) > 255:
-        raise RuntimeError("fused plan: more than 255 contributions to one slot in a tile")
+    if int(cnt.max()) > 0xFFFF:
+        raise RuntimeError("fused plan: too many contributions to one slot in a tile")
     ts_tile = uniq // nnz
     ts_gslot = uniq - ts_tile * nnz
-    cs = torch.cumsum(cnt, 0) - cnt                  # first contribution of each slot
-    kth = torch.arange(ncontrib, device=dev, dtype=i64) - cs[sinv]
+    kth = arange(ncontrib) - excl(cnt)[sinv]
     # within a tile, order slots by decreasing contribution count (sliced ELL)
-    order3 = torch.argsort(ts_tile * 256 + (255 - cnt), stable=True)
+    order3 = torch.argsort(ts_tile * 65536 + (65535 - cnt), stable=True)
     newpos = torch.empty(nts, dtype=i64, device=dev)
-    newpos[order3] = torch.arange(nts, device=dev, dtype=i64)
+    newpos[order3] = arange(nts)
     ts_tile, ts_gslot, cnt = ts_tile[order3], ts_gslot[order3], cnt[order3]
     tile_slot_start = torch.searchsorted(ts_tile, tile_ids)
     nslots_tile = tile_slot_start[1:] - tile_slot_start[:-1]
@@ -146,37 +159,19 @@ def build(basis, plan, T=1024, threads=256):
     tile_group_start = torch.cat([torch.zeros(1, dtype=i64, device=dev),
                                   torch.cumsum(ngroups_tile, 0)])
     ngroups = int(tile_group_start[-1])
-    ts_idx = torch.arange(nts, device=dev, dtype=i64)
+    ts_idx = arange(nts)
     j_in_tile = ts_idx - tile_slot_start[ts_tile]
     grp_of_slot = tile_group_start[ts_tile] + j_in_tile // 32
     lane_of_slot = j_in_tile % 32
     grp_len = torch.zeros(ngroups, dtype=i64, device=dev)
     grp_len.scatter_reduce_(0, grp_of_slot, cnt, reduce="amax", include_self=True)
-    # per-tile index regions, each starting at a multiple of 8 indices (16 B)
-    gsz_ids = grp_len * 32
-    gcum = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(gsz_ids, 0)])
-    tile_ids_n = gcum[tile_group_start[1:]] - gcum[tile_group_start[:-1]]   # multiple of 32
-    tile_contrib_start = torch.cat([torch.zeros(1, dtype=i64, device=dev),
-                                    torch.cumsum(tile_ids_n, 0)])
-    grp_tile = torch.repeat_interleave(torch.arange(ntiles, device=dev, dtype=i64),
-                                       ngroups_tile)
-    grp_base = gcum[:-1] - gcum[tile_group_start[:-1]][grp_tile]            # tile-relative
+    grp_tile = torch.repeat_interleave(arange(ntiles), ngroups_tile)
+    gcum = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(grp_len * 32, 0)])
+    nids_tile = gcum[tile_group_start[1:]] - gcum[tile_group_start[:-1]]   # multiples of 32
+    grp_base = gcum[:-1] - gcum[tile_group_start[:-1]][grp_tile]          # tile-relative
+    if int(grp_base.max()) // 32 > 0xFFFF:
+        raise RuntimeError("fused plan: tile index list too long")
     ncontrib_sell = int(gcum[-1])
-    s_new = newpos[sinv]
-    g_of = grp_of_slot[s_new]
-    cpos = tile_contrib_start[grp_tile[g_of]] + grp_base[g_of] + kth * 32 + lane_of_slot[s_new]
-    zero_idx = 10 * T                                 # staged 0.0: padding adds nothing
-    contrib = torch.full((max(ncontrib_sell, 8),), zero_idx, dtype=i64, device=dev)
-    contrib[cpos] = sid
-    fp.tile_slot_start = tile_slot_start.to(torch.int32).contiguous()
-    fp.tile_group_start = tile_group_start.to(torch.int32).contiguous()
-    fp.tile_contrib_start = tile_contrib_start.to(torch.int32).contiguous()
-    fp.grp_base = grp_base.to(torch.int32).contiguous()
-    fp.grp_len = grp_len.to(torch.int16).contiguous()
-    fp.contrib = contrib.to(torch.int16).contiguous()
-    max_ids = int(tile_ids_n.max()) if ntiles else 0
-    fp.aux_bytes = ((max(fp.vcap * 32, max_ids * 2, 16) + 15) // 16) * 16
-    del sid, contrib, cpos, s_new, kth, sinv
     # 5. slots touched by one tile go straight to csr_data, the others through scratch
     order2 = torch.argsort(ts_gslot * ntiles + ts_tile)  # by csr slot, tiles ascending
     g_sorted = ts_gslot[order2]
@@ -185,15 +180,12 @@ def build(basis, plan, T=1024, threads=256):
         raise RuntimeError("fused plan: CSR pattern has slots no element contributes to")
     shared = gcnt > 1
     gsz = gcnt * shared
-    gstart = torch.cumsum(gsz, 0) - gsz
-    gfirst = torch.cumsum(gcnt, 0) - gcnt
-    grp = torch.repeat_interleave(torch.arange(nnz, device=dev, dtype=i64), gcnt)
-    rank = ts_idx - gfirst[grp]
-    spos = gstart[grp] + rank
-    meta_sorted = torch.where(shared[grp], spos | 0x80000000, g_sorted)
+    gstart = excl(gsz)
+    gfirst = excl(gcnt)
+    grp = torch.repeat_interleave(arange(nnz), gcnt)
+    spos = gstart[grp] + (ts_idx - gfirst[grp])
     meta = torch.empty(nts, dtype=i64, device=dev)
-    meta[order2] = meta_sorted
-    fp.meta = meta.to(torch.int32).contiguous()
+    meta[order2] = torch.where(shared[grp], spos | 0x80000000, g_sorted)
     sh = torch.nonzero(shared).flatten()
     fp.nshared = int(sh.shape[0])
     fp.nscratch = int(gsz.sum())
@@ -201,27 +193,93 @@ def build(basis, plan, T=1024, threads=256):
     fp.sptr = torch.cat([gstart[sh], torch.tensor([fp.nscratch], device=dev, dtype=i64)]
                         ).to(torch.int32).contiguous()
     fp.scratch = torch.empty(max(fp.nscratch, 1), dtype=torch.float64, device=dev)
+    del order2, g_sorted, grp, spos
+    # 6. pack the per-tile records
+    HDR = 32
+    off_verts = HDR + 8 * T
+    off_grp = off_verts + 4 * ((nverts_tile + 3) // 4 * 4)
+    off_meta = off_grp + 16 * ((ngroups_tile + 3) // 4)
+    off_ids = off_meta + 128 * ngroups_tile
+    size = off_ids + 2 * nids_tile                   # multiple of 16
+    rec_start = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(size, 0)])
+    total = int(rec_start[-1])
+    fp.rec_cap = int(size.max())
+    buf32 = torch.zeros(total // 4, dtype=torch.int32, device=dev)
+    buf16 = buf32.view(torch.int16)
+    rs = rec_start[:-1]
+    hdr = torch.stack([nverts_tile, ngroups_tile, torch.full_like(rs, off_verts), off_grp,
+                       off_meta, off_ids, nslots_tile, size], dim=1)
+    buf32[(rs // 4)[:, None] + arange(8)[None, :]] = hdr.to(torch.int32)
+    # tl (padding elements of the last tile: 0xFFFF)
+    pad = ntiles * T - nel
+    if pad:
+        last = (int(rs[-1]) + HDR) // 2 + 4 * (T - pad)
+        buf16[last:last + 4 * pad] = -1
+    buf16[((rs[tile_of] + HDR) // 2 + 4 * e_loc)[:, None] + arange(4)[None, :]] = \
+        loc.to(torch.int16)
+    # verts
+    buf32[(rs[vert_tile] + off_verts) // 4 + vert_loc] = vert_gid.to(torch.int32)
+    # grp: offset/32 | len << 16
+    g_local = arange(ngroups) - tile_group_start[grp_tile]
+    gword = (grp_base // 32) | (grp_len << 16)
+    buf32[(rs[grp_tile] + off_grp[grp_tile]) // 4 + g_local] = gword.to(torch.int32)
+    # meta: unused lanes -> 0xFFFFFFFF, then the real ones
+    lanes = arange(32)
+    buf32[((rs[grp_tile] + off_meta[grp_tile]) // 4 + g_local * 32)[:, None] + lanes[None, :]] = -1
+    buf32[(rs[ts_tile] + off_meta[ts_tile]) // 4 + j_in_tile] = meta.to(torch.int32)
+    # ids: padding -> index of the staged zero, then the real contributions
+    zero_idx = 10 * T
+    tile_ids_start = excl(nids_tile)
+    id_tile = torch.repeat_interleave(arange(ntiles), nids_tile)
+    id_pos = (rs[id_tile] + off_ids[id_tile]) // 2 + (arange(ncontrib_sell) - tile_ids_start[id_tile])
+    buf16[id_pos] = torch.tensor(zero_idx, dtype=i64, device=dev).to(torch.int16)
+    del id_tile, id_pos
+    s_new = newpos[sinv]
+    g_of = grp_of_slot[s_new]
+    t_of = grp_tile[g_of]
+    cpos = (rs[t_of] + off_ids[t_of]) // 2 + grp_base[g_of] + kth * 32 + lane_of_slot[s_new]
+    buf16[cpos] = sid.to(torch.int16)
+    fp.rec = buf32
+    fp.rec_start = rec_start.contiguous()            # int64 == uint64 for the kernel
     fp.nts, fp.ncontrib, fp.ncontrib_sell, fp.ngroups = nts, ncontrib, ncontrib_sell, ngroups
-    fp.nverts_tiles = int(fp.tile_verts.shape[0])
+    fp.nverts_tiles = int(vert_gid.shape[0])
+    fp.rec_bytes = total
     fp.w = float(basis.W[0])
     fp.nqp = int(basis.nqp)
     fp.p = p
-    smem = 8 * (10 * T + 2) + fp.aux_bytes
-    if smem > 226 * 1024:
-        raise RuntimeError("fused plan: tile does not fit in shared memory")
+    fp.smem = int(_lib.lib().skb_p1_fused_smem_bytes(T, ring, fp.rec_cap, fp.vcap))
+    if fp.smem > 227 * 1024:
+        raise FusedPlanTooBig("fused plan: tile does not fit in shared memory "
+                              "({} B); use a smaller tile".format(fp.smem))
     return fp
+
+
+class FusedPlanTooBig(RuntimeError):
+    pass
+
+
+def build_auto(basis, plan, T=512, threads=256, ring=4):
+    """Build with the requested tile, halving it while the tile's record ring
+    and coordinates do not fit in shared memory (irregular meshes whose tiles
+    touch many vertices).  Returns None if even the smallest tile is too big:
+    the caller then stays on the generic path."""
+    options = [(T, threads)] + [c for c in ((512, 256), (256, 256), (256, 128))
+                                if c[0] < T]
+    for tile, thr in options:
+        try:
+            return build(basis, plan, T=tile, threads=thr, ring=ring)
+        except FusedPlanTooBig:
+            continue
+    return None
 
 
 def run(fp, data, stream):
     """Warm numeric phase: two kernel launches, nothing else."""
     lib = _lib.lib()
     code = lib.skb_p1tet_laplace_fused(
-        fp.p.data_ptr(), fp.p.shape[1], fp.tl.data_ptr(), fp.ntiles, fp.T, fp.threads,
-        fp.tile_vert_start.data_ptr(), fp.tile_verts.data_ptr(), fp.aux_bytes,
-        fp.tile_slot_start.data_ptr(), fp.tile_group_start.data_ptr(),
-        fp.tile_contrib_start.data_ptr(), fp.grp_base.data_ptr(), fp.grp_len.data_ptr(),
-        fp.contrib.data_ptr(), fp.meta.data_ptr(), C.c_double(fp.w), fp.nqp, data.data_ptr(),
-        fp.scratch.data_ptr(), stream)
+        fp.p.data_ptr(), fp.p.shape[1], fp.rec.data_ptr(), fp.rec_start.data_ptr(), fp.ntiles,
+        fp.T, fp.threads, fp.ring, fp.rec_cap, fp.vcap, C.c_double(fp.w), fp.nqp,
+        data.data_ptr(), fp.scratch.data_ptr(), stream)
     _lib.check(code, "skb_p1tet_laplace_fused")
     code = lib.skb_p1_combine(fp.scratch.data_ptr(), fp.sptr.data_ptr(), fp.gslot.data_ptr(),
                               fp.nshared, data.data_ptr(), stream)
@@ -231,15 +289,14 @@ def run(fp, data, stream):
 def stats(fp):
     """Bytes the fused step moves (for DESIGN.md / the roofline discussion)."""
     b = {
-        "tl": fp.ntiles * fp.T * 8, "tile_verts": fp.nverts_tiles * 4,
-        "p_gather_min": fp.nverts_tiles * 24, "contrib": fp.ncontrib_sell * 2,
-        "meta": fp.nts * 4, "groups": fp.ngroups * 6,
+        "records": fp.rec_bytes, "p_gather_min": fp.nverts_tiles * 24,
         "direct_out": (fp.nnz - fp.nshared) * 8, "scratch_w": fp.nscratch * 8,
-        "scratch_r": fp.nscratch * 8, "sptr_gslot": fp.nshared * 8, "combine_out": fp.nshared * 8,
+        "scratch_r": fp.nscratch * 8, "sptr_gslot": fp.nshared * 8,
+        "combine_out": fp.nshared * 8,
     }
     b["total"] = sum(b.values())
     b["per_element"] = b["total"] / max(fp.nel, 1)
     b["tile_slots_per_csr_slot"] = fp.nts / max(fp.nnz, 1)
-    b["vcap"] = fp.vcap
+    b["vcap"], b["rec_cap"], b["smem"] = fp.vcap, fp.rec_cap, fp.smem
     b["sell_padding"] = fp.ncontrib_sell / max(fp.ncontrib, 1)
     return b

@@ -185,14 +185,15 @@ def test_quadrature_mismatch_errors():
         laplace.assemble(b1, b2)
 
 
-@pytest.mark.parametrize("tile,threads", [(1024, 256), (1024, 512), (2048, 512), (512, 256)])
-def test_fused_p1_path(tile, threads):
+@pytest.mark.parametrize("tile,threads,ring", [(512, 256, 4), (512, 512, 5), (512, 128, 4),
+                                               (256, 128, 5), (256, 256, 4), (768, 256, 4)])
+def test_fused_p1_path(tile, threads, ring):
     """Warm re-assembly goes through the fused kernel (csrc/skb_p1_fused.cu):
     same plan (indptr/indices bit-exact), values within rtol 1e-12 of the
     reference, bit-identical between repeated runs."""
     from skfem_b200.models.poisson import laplace
     from skfem_b200 import form as F
-    F.set_options(fused=True, fused_tile=tile, fused_threads=threads)
+    F.set_options(fused=True, fused_tile=tile, fused_threads=threads, fused_ring=ring)
     try:
         for name in ["tet_p1_tensor6", "tet_p1_ball2", "tet_p1_refined3", "tet_p1_morphed5",
                      "tet_p1_tensor_nonuniform"]:
@@ -200,7 +201,7 @@ def test_fused_p1_path(tile, threads):
             b = fem.Basis(mesh_from(g, "tet"), fem.ElementTetP1())
             A0 = laplace.assemble(b)                      # cold, generic path
             A1 = laplace.assemble(b)                      # warm, fused path
-            assert ("fused", laplace._plan_key(b, None, {})) in b._plans
+            assert b._plans[("fused", laplace._plan_key(b, None, {}))] is not None
             A2 = laplace.assemble(b)
             _check_csr(A1, g, "laplace")
             assert np.array_equal(A1.data, A2.data)
@@ -220,7 +221,7 @@ def test_fused_p1_path(tile, threads):
         assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
         np.testing.assert_allclose(A.data, Ao.data, rtol=RTOL, atol=RTOL * np.abs(Ao.data).max())
         fp = b._plans[("fused", laplace._plan_key(b, None, {}))]
-        assert fp.ntiles == -(-m.nelements // tile) and fp.nshared > 0
+        assert fp.ntiles == -(-m.nelements // fp.T) and fp.nshared > 0 and fp.T <= tile
         # element subset
         sub = np.arange(0, m.nelements, 3)
         bs = fem.Basis(m, fem.ElementTetP1(), elements=sub)
@@ -232,4 +233,4 @@ def test_fused_p1_path(tile, threads):
         np.testing.assert_allclose(As.data, Aso.data, rtol=RTOL,
                                    atol=RTOL * np.abs(Aso.data).max())
     finally:
-        F.set_options(fused=True, fused_tile=1024, fused_threads=256)
+        F.set_options(fused=True, fused_tile=512, fused_threads=256, fused_ring=4)
