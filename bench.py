@@ -174,6 +174,8 @@ def run_gpu(args):
     nnz = A.nnz
 
     out = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    if args.debug_flags:
+        _lib.lib().skb_debug_flags(args.debug_flags)   # profiling only: results invalid
 
     def step_eager():
         return laplace.assemble_device(basis, out=out)
@@ -312,13 +314,16 @@ def main():
                     help="cells per side of the CPU sample (60 -> 1.3 M tets)")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    ap.add_argument("--debug-flags", type=int, default=0, dest="debug_flags",
+                    help="profiling aid (skb_debug_flags): 1 skip P1, 2 skip P2; invalid results")
     ap.add_argument("--no-graph", action="store_true", dest="no_graph",
                     help="launch the warm step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-fused", action="store_true", dest="no_fused",
                     help="time the generic two-kernel path instead of the fused P1 kernel")
     ap.add_argument("--tile", type=int, default=512)
     ap.add_argument("--ring", type=int, default=4)
-    ap.add_argument("--threads", type=int, default=256)
+    ap.add_argument("--threads", type=int, default=480,
+                    help="reduce threads per CTA of the fused kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

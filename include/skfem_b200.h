@@ -140,20 +140,30 @@ int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *se
  * threads per CTA; records stream through a ring of `ring` (4|5) shared
  * buffers of rec_cap bytes by TMA bulk copies, vertex coordinates are gathered
  * with cp.async; vcap = most vertices in a tile.  (tile_elems, reduce_threads)
- * in {(256,128) (256,256) (512,128) (512,256) (512,512) (768,256)}.
+ * in {(256,128) (256,256) (512,128) (512,256) (512,384) (512,480) (768,224)};
+ * one more warp per CTA issues the TMA copies.
  * skb_p1_fused_smem_bytes gives the dynamic shared memory a configuration
- * needs (must be <= 227 KB).  w = the common quadrature weight (all weights of
+ * needs (must be <= 227 KB).  tame != 0 asserts that every vertex coordinate is
+ * 0 or within [2^-60, 2^60] in magnitude, which lets the kernel use its
+ * shared-reciprocal exact division without per-element range checks (tame == 0
+ * selects plain IEEE division).  w = the common quadrature weight (all weights of
  * the rule must be equal), nqp = number of quadrature points.  skb_p1_combine
  * adds, in tile order, the per-tile partial sums of CSR slots touched by more
  * than one tile.  No float atomics: bit-reproducible.                        */
+/* profiling aid for skb_p1tet_laplace_fused: bit0 skips the local-matrix phase,
+ * bit1 the slot-reduction phase (results are then meaningless). Default 0.  */
+void skb_debug_flags(int flags);
 int64_t skb_p1_fused_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap, int32_t vcap);
 int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void *rec,
                             const uint64_t *rec_start, int32_t ntiles, int32_t tile_elems,
                             int32_t reduce_threads, int32_t ring, int32_t rec_cap, int32_t vcap,
-                            double w, int32_t nqp, double *csr_data, double *scratch,
-                            void *stream);
+                            int32_t tame, double w, int32_t nqp, double *csr_data,
+                            double *scratch, void *stream);
+/* The Laplace local matrix is bitwise symmetric, so only canonical slots
+ * (row <= col) are reduced; gslot2[k] is the mirror CSR slot (col,row) that
+ * receives the same sum (== gslot[k] on the diagonal).                       */
 int skb_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
-                   int64_t nshared, double *csr_data, void *stream);
+                   const uint32_t *gslot2, int64_t nshared, double *csr_data, void *stream);
 
 /* ---- materialised basis for traced (user-defined) forms -----------------
  * grad: (dim, nel, nqp) of scalar basis function b (element_h1.py:17);

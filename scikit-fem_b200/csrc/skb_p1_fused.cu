@@ -47,10 +47,12 @@ struct P1Args {
   double *scratch;
   double w;                     // the common quadrature weight
   int32_t nqp;
+  int32_t tame;                 // all coordinates within the exact_div-safe range
+  int32_t debug;                // profiling aid: bit0 skip P1, bit1 skip P2 (results invalid)
 };
 
 struct RecHeader {              // 32 bytes at the start of every record
-  uint32_t nverts, ngroups, off_verts, off_grp, off_meta, off_ids, nslots, bytes;
+  uint32_t nverts, ngroups, off_verts, off_grp, off_meta, off_ids, nslots, off_meta2;
 };
 
 __device__ __forceinline__ constexpr int sym_index4(int a, int b) {  // a <= b
@@ -74,15 +76,12 @@ __device__ __forceinline__ double sum_equal_terms(double v, int nqp) {
   return sum_equal_terms_general(v, nqp);
 }
 
-// |c| is 0 or within [2^-60, 2^60]: if every coordinate of a tile passes, all
-// cofactors are 0 or in [2^-278, 2^123] and a nonzero determinant lies in
-// [2^-443, 2^186], so exact_div() can neither overflow nor underflow and no
-// per-element exponent checks are needed ("exact division").
-__device__ __forceinline__ bool coord_tame(double c) {
-  const unsigned h = (unsigned)__double2hiint(c) & 0x7fffffffu;
-  const bool zero = (h | (unsigned)__double2loint(c)) == 0u;
-  return zero | ((h - 0x3c300000u) <= (0x43b00000u - 0x3c300000u));
-}
+// P1Args::tame: the plan builder verified that every vertex coordinate is 0 or
+// has magnitude within [2^-60, 2^60].  Then all cofactors are 0 or in
+// [2^-278, 2^123] and a nonzero determinant lies in [2^-443, 2^186], so
+// exact_div() can neither overflow nor underflow and no per-element exponent
+// checks are needed ("exact division").  Otherwise every element
+// takes the plain IEEE division.
 
 // ---- async-copy / mbarrier primitives (PTX) ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -135,33 +134,47 @@ __device__ __forceinline__ void fence_proxy_async() {
 // barrier per iteration, then one thread re-arms the freed record buffer with
 // the TMA fetch of tile k-1+NR.
 template <int T_ELEMS, int NRED, int NR, bool NQP4>
-__global__ void __launch_bounds__(T_ELEMS + NRED)
+__global__ void __launch_bounds__(T_ELEMS + NRED + 32)
 p1tet_laplace_fused_kernel(const P1Args a) {
   static_assert(NR >= 4, "record ring must hold tiles k-1 .. k+2");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int VSTRIDE = 10 * T_ELEMS + 2;
   // shared layout: vals[2] | coords[3] | records[NR] | mbarriers | flags | counters
   double *vals = reinterpret_cast<double *>(smem_raw);                      // [2][VSTRIDE]
-  double4 *coords = reinterpret_cast<double4 *>(vals + 2 * VSTRIDE);        // [3][vcap]
-  unsigned char *recs = reinterpret_cast<unsigned char *>(coords + 3 * a.vcap);
+  // coordinates: 3 buffers x {x[vcap], y[vcap], z[vcap]} (struct of arrays: a
+  // random 8-byte gather conflicts far less than a 32-byte-strided one)
+  double *coords = vals + 2 * VSTRIDE;                                      // [3][3][vcap]
+  unsigned char *recs = reinterpret_cast<unsigned char *>(coords + 9 * (size_t)a.vcap);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(recs + (size_t)NR * a.rec_cap);
-  int *s_wild = reinterpret_cast<int *>(mbar + NR);                         // [3]
-  int *s_next = s_wild + 3;                                                 // [2]
+  // roles: [0, T) compute, [T, T+NRED) reduce, last warp = TMA producer (lane 0)
   const bool is_compute = threadIdx.x < T_ELEMS;
+  const bool is_reduce = !is_compute && threadIdx.x < T_ELEMS + NRED;
+  const bool is_producer = threadIdx.x == T_ELEMS + NRED;
   const int rtid = (int)threadIdx.x - T_ELEMS;        // reduce-thread index
   const int lane = threadIdx.x & 31;
+  const int rwarp = rtid >> 5;                        // reduce-warp index
+  constexpr int NRW = NRED / 32;
+  const bool tame = a.tame != 0;
   const int nk = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
   auto rec_of = [&](int k) { return recs + (size_t)(k % NR) * a.rec_cap; };
-  auto issue = [&](int k) {   // one thread: fetch the record of this CTA's k-th tile
+  // producer lane: record extents are loaded one iteration before they are
+  // needed so the TMA issue after the barrier has no global-load latency
+  uint64_t nx_b0 = 0;
+  unsigned nx_bytes = 0;
+  auto extent = [&](int k) {
     if (k < nk) {
       const int t = tile_of(k);
-      const uint64_t b0 = a.rec_start[t];
-      const unsigned bytes = (unsigned)(a.rec_start[t + 1] - b0);
+      nx_b0 = a.rec_start[t];
+      nx_bytes = (unsigned)(a.rec_start[t + 1] - nx_b0);
+    }
+  };
+  auto issue = [&](int k) {   // fetch the record of this CTA's k-th tile (extent preloaded)
+    if (k < nk) {
       fence_proxy_async();
-      mbar_expect_tx(&mbar[k % NR], bytes);
-      tma_bulk_g2s(rec_of(k), a.rec + b0, bytes, &mbar[k % NR]);
+      mbar_expect_tx(&mbar[k % NR], nx_bytes);
+      tma_bulk_g2s(rec_of(k), a.rec + nx_b0, nx_bytes, &mbar[k % NR]);
     }
   };
   auto wait_rec = [&](int k) { mbar_wait(&mbar[k % NR], (unsigned)((k / NR) & 1)); };
@@ -170,25 +183,14 @@ p1tet_laplace_fused_kernel(const P1Args a) {
     const RecHeader *h = reinterpret_cast<const RecHeader *>(r);
     const int nv = (int)h->nverts;
     const int32_t *verts = reinterpret_cast<const int32_t *>(r + h->off_verts);
-    double4 *dst = coords + (size_t)(k % 3) * a.vcap;
+    double *dx = coords + (size_t)(k % 3) * 3 * a.vcap, *dy = dx + a.vcap, *dz = dy + a.vcap;
     const double *px = a.p, *py = a.p + a.npts, *pz = a.p + 2 * a.npts;
     for (int i = rtid; i < nv; i += NRED) {
       const int32_t gv = verts[i];
-      cp_async8(&dst[i].x, px + gv);
-      cp_async8(&dst[i].y, py + gv);
-      cp_async8(&dst[i].z, pz + gv);
+      cp_async8(dx + i, px + gv);
+      cp_async8(dy + i, py + gv);
+      cp_async8(dz + i, pz + gv);
     }
-  };
-  auto check_tame = [&](int k) {  // reduce threads, after their copies of tile k landed
-    const RecHeader *h = reinterpret_cast<const RecHeader *>(rec_of(k));
-    const int nv = (int)h->nverts;
-    const double4 *src = coords + (size_t)(k % 3) * a.vcap;
-    bool wild = false;
-    for (int i = rtid; i < nv; i += NRED) {
-      const double4 c = src[i];
-      wild |= !(coord_tame(c.x) & coord_tame(c.y) & coord_tame(c.z));
-    }
-    if (wild) s_wild[k % 3] = 1;
   };
 
   if (threadIdx.x == 0) {
@@ -196,45 +198,43 @@ p1tet_laplace_fused_kernel(const P1Args a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     vals[10 * T_ELEMS] = 0.0;
     vals[VSTRIDE + 10 * T_ELEMS] = 0.0;
-    s_wild[0] = s_wild[1] = s_wild[2] = 0;
-    s_next[0] = s_next[1] = 0;
   }
   __syncthreads();
   if (nk <= 0) return;
   // prologue: records 0..NR-2 in flight, coordinates of tiles 0 and 1 resident
-  if (threadIdx.x == 0)
-    for (int k = 0; k < NR; ++k) issue(k);
-  if (!is_compute) {
+  if (is_producer) {
+    for (int k = 0; k < NR; ++k) { extent(k); issue(k); }
+    extent(NR);                        // for the issue after iteration 1
+  }
+  if (is_reduce) {
     wait_rec(0);
     gather(0);
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (nk > 1) { wait_rec(1); gather(1); }
     asm volatile("cp.async.commit_group;" ::: "memory");
     cp_async_wait_all();
-    check_tame(0);
-    if (nk > 1) check_tame(1);
   }
   __syncthreads();
 
   for (int k = 0; k <= nk; ++k) {
     if (is_compute) {
       // ---- P1(k): local matrices of tile k -> vals[k & 1] ---------------------------
-      if (k < nk) {
+      if (k < nk && !(a.debug & 1)) {
         wait_rec(k);
         const unsigned char *r = rec_of(k);
-        const bool tame = (s_wild[k % 3] == 0);
         const ushort4 *tl = reinterpret_cast<const ushort4 *>(r + sizeof(RecHeader));
-        const double4 *xyz = coords + (size_t)(k % 3) * a.vcap;
+        const double *sx = coords + (size_t)(k % 3) * 3 * a.vcap, *sy = sx + a.vcap,
+                     *sz = sy + a.vcap;
         double *out = vals + (size_t)(k & 1) * VSTRIDE;
         const int el = threadIdx.x;
         const ushort4 v = tl[el];
         if (v.x != 0xFFFF) {  // not a padding element of the last tile
           double A[3][3];
           {
-            const double4 q0 = xyz[v.x], q1 = xyz[v.y], q2 = xyz[v.z], q3 = xyz[v.w];
-            A[0][0] = q1.x - q0.x; A[0][1] = q2.x - q0.x; A[0][2] = q3.x - q0.x;
-            A[1][0] = q1.y - q0.y; A[1][1] = q2.y - q0.y; A[1][2] = q3.y - q0.y;
-            A[2][0] = q1.z - q0.z; A[2][1] = q2.z - q0.z; A[2][2] = q3.z - q0.z;
+            const double x0 = sx[v.x], y0 = sy[v.x], z0 = sz[v.x];
+            A[0][0] = sx[v.y] - x0; A[0][1] = sx[v.z] - x0; A[0][2] = sx[v.w] - x0;
+            A[1][0] = sy[v.y] - y0; A[1][1] = sy[v.z] - y0; A[1][2] = sy[v.w] - y0;
+            A[2][0] = sz[v.y] - z0; A[2][1] = sz[v.z] - z0; A[2][2] = sz[v.w] - z0;
           }
           const double det = det3(A);
           double n[3][3], inv[3][3];
@@ -271,13 +271,9 @@ p1tet_laplace_fused_kernel(const P1Args a) {
             }
         }
       }
-    } else {
+    } else if (is_reduce) {
       // ---- reduce warps -----------------------------------------------------------------
-      if (rtid == 0) {
-        s_next[(k + 1) & 1] = 0;      // counter of the next iteration's P2
-        s_wild[(k + 2) % 3] = 0;      // flag of tile k+2 (last read for tile k-1)
-      }
-      if (k >= 1) {
+      if (k >= 1 && !(a.debug & 2)) {
         // ---- P2(k-1): per-slot sums in fixed order (sliced ELL, in shared memory) -----
         const unsigned char *r = rec_of(k - 1);
         const RecHeader *h = reinterpret_cast<const RecHeader *>(r);
@@ -285,33 +281,32 @@ p1tet_laplace_fused_kernel(const P1Args a) {
         const int ngroups = (int)h->ngroups;
         const uint32_t *grp = reinterpret_cast<const uint32_t *>(r + h->off_grp);
         const uint32_t *meta = reinterpret_cast<const uint32_t *>(r + h->off_meta);
+        const uint32_t *meta2 = reinterpret_cast<const uint32_t *>(r + h->off_meta2);
         const uint16_t *ids = reinterpret_cast<const uint16_t *>(r + h->off_ids);
-        int *counter = &s_next[k & 1];
-        for (;;) {  // groups are sorted longest first: dynamic hand-out balances the warps
-          int g = 0;
-          if (lane == 0) g = atomicAdd(counter, 1);
-          g = __shfl_sync(0xffffffffu, g, 0);
-          if (g >= ngroups) break;
+        // groups are sorted longest first, dealt round-robin to the reduce warps;
+        // every list length is a multiple of 2 (padded with the staged zero)
+#pragma unroll 1
+        for (int g = rwarp; g < ngroups; g += NRW) {
           const uint32_t gi = grp[g];
           const int len = (int)(gi >> 16);
           const uint16_t *cb = ids + (size_t)(gi & 0xffffu) * 32 + lane;
           const uint32_t m = meta[g * 32 + lane];
+          const uint32_t m2 = meta2[g * 32 + lane];
           double acc = 0.0;
-          int c = 0;
-          for (; c + 4 <= len; c += 4) {
-            const int i0 = cb[c * 32], i1 = cb[(c + 1) * 32], i2 = cb[(c + 2) * 32],
-                      i3 = cb[(c + 3) * 32];
-            const double a0 = in[i0], a1 = in[i1], a2 = in[i2], a3 = in[i3];
+#pragma unroll 2
+          for (int c = 0; c < len; c += 2) {
+            const int i0 = cb[c * 32], i1 = cb[(c + 1) * 32];
+            const double a0 = in[i0], a1 = in[i1];
             acc = acc + a0;
             acc = acc + a1;
-            acc = acc + a2;
-            acc = acc + a3;
           }
-          for (; c < len; ++c) acc = acc + in[cb[c * 32]];
+          // the local matrix is bitwise symmetric: slot (r,c), r<c, and its
+          // mirror (c,r) receive the same terms in the same order -> one sum
           if (m != 0xffffffffu) {
             if (m & 0x80000000u) a.scratch[m & 0x7fffffffu] = acc;
             else a.csr_data[m] = acc;
           }
+          if (m2 != 0xffffffffu) a.csr_data[m2] = acc;
         }
       }
       // request the vertex gather of tile k+2 (its record has been in flight
@@ -323,53 +318,69 @@ p1tet_laplace_fused_kernel(const P1Args a) {
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");
-      if (k >= 1 && k + 1 < nk) check_tame(k + 1);
     }
     __syncthreads();  // vals[k&1] complete; record k-1 free; coords of tile k+1 visible
-    if (threadIdx.x == 0 && k >= 1) issue(k - 1 + NR);  // into the buffer tile k-1 vacated
+    if (is_producer && k >= 1) {
+      issue(k - 1 + NR);               // into the buffer tile k-1 vacated
+      extent(k + NR);                  // its latency hides behind the next iteration
+    }
   }
 }
 
 __global__ void __launch_bounds__(256)
 p1_combine_kernel(const double *__restrict__ scratch, const uint32_t *__restrict__ sptr,
-                  const uint32_t *__restrict__ gslot, int64_t nshared,
-                  double *__restrict__ csr_data) {
+                  const uint32_t *__restrict__ gslot, const uint32_t *__restrict__ gslot2,
+                  int64_t nshared, double *__restrict__ csr_data) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nshared;
        k += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t a = sptr[k], b = sptr[k + 1];
     double acc = scratch[a];
     for (uint32_t i = a + 1; i < b; ++i) acc = acc + scratch[i];
-    csr_data[gslot[k]] = acc;
+    const uint32_t s = gslot[k], s2 = gslot2[k];
+    csr_data[s] = acc;
+    if (s2 != s) csr_data[s2] = acc;   // mirror slot of a symmetric pair
   }
 }
 
+static int g_debug = 0;
+
 template <int TT, int NRED, int NR>
 static int launch_fused(const P1Args &a, size_t smem, int sms, bool q4, cudaStream_t st) {
-  const int grid = a.ntiles < sms ? a.ntiles : sms;
+  // persistent grid: as many CTAs per SM as shared memory, threads and
+  // registers (<= 64 per thread by __launch_bounds__) allow
+  int per_sm = (int)((228 * 1024) / (smem + 1024));
+  const int by_threads = 2048 / (TT + NRED + 32);
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm < 1) per_sm = 1;
+  const int cap = per_sm * sms;
+  const int grid = a.ntiles < cap ? a.ntiles : cap;
   if (q4) {
     auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, true>;
     SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, TT + NRED, smem, st>>>(a);
+    k<<<grid, TT + NRED + 32, smem, st>>>(a);
   } else {
     auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, false>;
     SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, TT + NRED, smem, st>>>(a);
+    k<<<grid, TT + NRED + 32, smem, st>>>(a);
   }
   return (int)cudaGetLastError();
 }
 
 }  // namespace skb
 
+extern "C" void skb_debug_flags(int flags) { skb::g_debug = flags; }
+
 extern "C" int64_t skb_p1_fused_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap,
                                            int32_t vcap) {
-  return (int64_t)(sizeof(double) * 2 * (10 * (size_t)tile_elems + 2) + 3 * (size_t)vcap * 32 +
+  return (int64_t)(sizeof(double) * 2 * (10 * (size_t)tile_elems + 2) + 9 * (size_t)vcap * 8 +
                    (size_t)ring * rec_cap + 8 * (size_t)ring + 32);
 }
 
 extern "C" int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void *rec,
                                        const uint64_t *rec_start, int32_t ntiles,
                                        int32_t tile_elems, int32_t reduce_threads, int32_t ring,
-                                       int32_t rec_cap, int32_t vcap, double w, int32_t nqp,
+                                       int32_t rec_cap, int32_t vcap, int32_t tame, double w,
+                                       int32_t nqp,
                                        double *csr_data, double *scratch, void *stream) {
   using namespace skb;
   if (ntiles < 0 || !p || nqp <= 0 || vcap <= 0 || rec_cap <= 0 || (rec_cap & 15)) return SKB_EINVAL;
@@ -377,7 +388,8 @@ extern "C" int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void
   P1Args a;
   a.p = p; a.npts = npts; a.rec = (const unsigned char *)rec; a.rec_start = rec_start;
   a.ntiles = ntiles; a.rec_cap = rec_cap; a.vcap = vcap;
-  a.csr_data = csr_data; a.scratch = scratch; a.w = w; a.nqp = nqp;
+  a.csr_data = csr_data; a.scratch = scratch; a.w = w; a.nqp = nqp; a.tame = tame;
+  a.debug = g_debug;
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -391,26 +403,32 @@ extern "C" int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void
     if (ring == 4) rc = launch_fused<TT, NRED, 4>(a, smem, sms, q4, st);       \
     else if (ring == 5) rc = launch_fused<TT, NRED, 5>(a, smem, sms, q4, st);  \
   }
+  SKB_P1_CASE(128, 96)
   SKB_P1_CASE(256, 128)
+  SKB_P1_CASE(256, 224)
   SKB_P1_CASE(256, 256)
+  SKB_P1_CASE(384, 224)
+  SKB_P1_CASE(384, 352)
   SKB_P1_CASE(512, 128)
   SKB_P1_CASE(512, 256)
-  SKB_P1_CASE(512, 512)
-  SKB_P1_CASE(768, 256)
+  SKB_P1_CASE(512, 384)
+  SKB_P1_CASE(512, 480)
+  SKB_P1_CASE(768, 224)
 #undef SKB_P1_CASE
   if (rc == SKB_OK) count_launch();
   return rc;
 }
 
 extern "C" int skb_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
-                              int64_t nshared, double *csr_data, void *stream) {
+                              const uint32_t *gslot2, int64_t nshared, double *csr_data,
+                              void *stream) {
   using namespace skb;
   if (nshared < 0) return SKB_EINVAL;
   if (nshared == 0) return SKB_OK;
   int64_t g = (nshared + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  p1_combine_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(scratch, sptr, gslot, nshared,
-                                                              csr_data);
+  p1_combine_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(scratch, sptr, gslot, gslot2,
+                                                              nshared, csr_data);
   count_launch();
   return (int)cudaGetLastError();
 }

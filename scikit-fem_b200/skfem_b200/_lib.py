@@ -48,9 +48,10 @@ SIGNATURES = {
     "skb_tabulate": (_INT, [_SP, _INT, _P, _P, _P, _P, _P]),
     "skb_qp_reduce": (_INT, [_P, _P, _I64, _I32, _INT, _P, _P]),
     "skb_p1tet_laplace_fused": (_INT, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32,
-                                       C.c_double, _I32, _P, _P, _P]),
+                                       _I32, C.c_double, _I32, _P, _P, _P]),
     "skb_p1_fused_smem_bytes": (_I64, [_I32, _I32, _I32, _I32]),
-    "skb_p1_combine": (_INT, [_P, _P, _P, _I64, _P, _P]),
+    "skb_debug_flags": (None, [_INT]),
+    "skb_p1_combine": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "skb_launch_count": (_I64, [_INT]),
     "skb_version": (C.c_char_p, []),
 }

@@ -44,7 +44,7 @@ def _torch():
     return torch
 
 
-_CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 256, "fused_ring": 4}
+_CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring": 4}
 
 
 def set_options(**kw):

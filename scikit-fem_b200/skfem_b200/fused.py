@@ -67,7 +67,7 @@ def applicable(basis, form):
     return bool(np.all(W == W[0]))
 
 
-def build(basis, plan, T=512, threads=256, ring=2):
+def build(basis, plan, T=512, threads=480, ring=4):
     torch = _torch()
     d = basis._dev()
     dev = d["device"]
@@ -109,7 +109,7 @@ def build(basis, plan, T=512, threads=256, ring=2):
     uv_tile = uv // nv
     tile_vert_start = torch.searchsorted(uv_tile, tile_ids)
     nverts_tile = tile_vert_start[1:] - tile_vert_start[:-1]
-    fp.vcap = int(nverts_tile.max())
+    fp.vcap = (int(nverts_tile.max()) + 1) // 2 * 2   # even: keeps shared sections 16 B aligned
     if fp.vcap >= 0xFFFF:
         raise RuntimeError("fused plan: tile touches too many vertices")
     loc = (vinv - tile_vert_start[tile_of].repeat_interleave(4)).reshape(nel, 4)
@@ -120,16 +120,25 @@ def build(basis, plan, T=512, threads=256, ring=2):
     # 3. CSR slot of every local entry (a, b)
     counts = (plan.indptr[1:] - plan.indptr[:-1]).long()
     row_of_slot = torch.repeat_interleave(arange(N), counts)
-    csr_key = row_of_slot * N + plan.indices.long()  # ascending (canonical CSR)
-    del row_of_slot
+    cols = plan.indices.long()
+    csr_key = row_of_slot * N + cols                 # ascending (canonical CSR)
+    # the Laplace local matrix is bitwise symmetric, hence so are the zero
+    # mask and the pattern: slot (r,c) and its mirror (c,r) receive identical
+    # terms.  Only canonical slots (row <= col) are reduced; the kernel writes
+    # the sum to the mirror slot too.
+    mirror = torch.searchsorted(csr_key, cols * N + row_of_slot).clamp(max=max(nnz - 1, 0))
+    if not bool((csr_key[mirror] == cols * N + row_of_slot).all()):
+        raise FusedPlanTooBig("fused plan: CSR pattern is not structurally symmetric")
+    n_canonical = int((row_of_slot <= cols).sum())
+    del row_of_slot, cols
     keys2, sids = [], []
     for a in range(4):
-        for b in range(4):
-            key = tt[:, a] * N + tt[:, b]            # row = test dof (v), col = trial dof (u)
+        for b in range(a, 4):
+            ra, rb = tt[:, a], tt[:, b]
+            key = torch.minimum(ra, rb) * N + torch.maximum(ra, rb)
             pos = torch.searchsorted(csr_key, key).clamp(max=max(nnz - 1, 0))
             ok = csr_key[pos] == key
-            lo_, hi_ = (a, b) if a <= b else (b, a)
-            k = lo_ * 4 - (lo_ * (lo_ - 1)) // 2 + (hi_ - lo_)
+            k = a * 4 - (a * (a - 1)) // 2 + (b - a)
             keys2.append((tile_of * nnz + pos)[ok])
             sids.append((k * T + e_loc)[ok])
     key2 = torch.cat(keys2)
@@ -165,6 +174,7 @@ def build(basis, plan, T=512, threads=256, ring=2):
     lane_of_slot = j_in_tile % 32
     grp_len = torch.zeros(ngroups, dtype=i64, device=dev)
     grp_len.scatter_reduce_(0, grp_of_slot, cnt, reduce="amax", include_self=True)
+    grp_len = (grp_len + 1) // 2 * 2                 # the kernel's P2 loop is unrolled by 2
     grp_tile = torch.repeat_interleave(arange(ntiles), ngroups_tile)
     gcum = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(grp_len * 32, 0)])
     nids_tile = gcum[tile_group_start[1:]] - gcum[tile_group_start[:-1]]   # multiples of 32
@@ -176,20 +186,28 @@ def build(basis, plan, T=512, threads=256, ring=2):
     order2 = torch.argsort(ts_gslot * ntiles + ts_tile)  # by csr slot, tiles ascending
     g_sorted = ts_gslot[order2]
     ug, gcnt = torch.unique_consecutive(g_sorted, return_counts=True)
-    if int(ug.shape[0]) != nnz:
+    if int(ug.shape[0]) != n_canonical:
         raise RuntimeError("fused plan: CSR pattern has slots no element contributes to")
     shared = gcnt > 1
     gsz = gcnt * shared
     gstart = excl(gsz)
     gfirst = excl(gcnt)
-    grp = torch.repeat_interleave(arange(nnz), gcnt)
+    grp = torch.repeat_interleave(arange(int(ug.shape[0])), gcnt)
     spos = gstart[grp] + (ts_idx - gfirst[grp])
+    NONE = 0xFFFFFFFF
     meta = torch.empty(nts, dtype=i64, device=dev)
     meta[order2] = torch.where(shared[grp], spos | 0x80000000, g_sorted)
+    # mirror target: written by the tile only for exclusive off-diagonal slots
+    # (shared ones are mirrored by skb_p1_combine)
+    mir_sorted = mirror[g_sorted]
+    meta2 = torch.empty(nts, dtype=i64, device=dev)
+    meta2[order2] = torch.where(shared[grp] | (mir_sorted == g_sorted),
+                                torch.full_like(g_sorted, NONE), mir_sorted)
     sh = torch.nonzero(shared).flatten()
     fp.nshared = int(sh.shape[0])
     fp.nscratch = int(gsz.sum())
-    fp.gslot = sh.to(torch.int32).contiguous()
+    fp.gslot = ug[sh].to(torch.int32).contiguous()
+    fp.gslot2 = mirror[ug[sh]].to(torch.int32).contiguous()
     fp.sptr = torch.cat([gstart[sh], torch.tensor([fp.nscratch], device=dev, dtype=i64)]
                         ).to(torch.int32).contiguous()
     fp.scratch = torch.empty(max(fp.nscratch, 1), dtype=torch.float64, device=dev)
@@ -199,7 +217,8 @@ def build(basis, plan, T=512, threads=256, ring=2):
     off_verts = HDR + 8 * T
     off_grp = off_verts + 4 * ((nverts_tile + 3) // 4 * 4)
     off_meta = off_grp + 16 * ((ngroups_tile + 3) // 4)
-    off_ids = off_meta + 128 * ngroups_tile
+    off_meta2 = off_meta + 128 * ngroups_tile
+    off_ids = off_meta2 + 128 * ngroups_tile
     size = off_ids + 2 * nids_tile                   # multiple of 16
     rec_start = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(size, 0)])
     total = int(rec_start[-1])
@@ -208,7 +227,7 @@ def build(basis, plan, T=512, threads=256, ring=2):
     buf16 = buf32.view(torch.int16)
     rs = rec_start[:-1]
     hdr = torch.stack([nverts_tile, ngroups_tile, torch.full_like(rs, off_verts), off_grp,
-                       off_meta, off_ids, nslots_tile, size], dim=1)
+                       off_meta, off_ids, nslots_tile, off_meta2], dim=1)
     buf32[(rs // 4)[:, None] + arange(8)[None, :]] = hdr.to(torch.int32)
     # tl (padding elements of the last tile: 0xFFFF)
     pad = ntiles * T - nel
@@ -227,6 +246,8 @@ def build(basis, plan, T=512, threads=256, ring=2):
     lanes = arange(32)
     buf32[((rs[grp_tile] + off_meta[grp_tile]) // 4 + g_local * 32)[:, None] + lanes[None, :]] = -1
     buf32[(rs[ts_tile] + off_meta[ts_tile]) // 4 + j_in_tile] = meta.to(torch.int32)
+    buf32[((rs[grp_tile] + off_meta2[grp_tile]) // 4 + g_local * 32)[:, None] + lanes[None, :]] = -1
+    buf32[(rs[ts_tile] + off_meta2[ts_tile]) // 4 + j_in_tile] = meta2.to(torch.int32)
     # ids: padding -> index of the staged zero, then the real contributions
     zero_idx = 10 * T
     tile_ids_start = excl(nids_tile)
@@ -247,6 +268,10 @@ def build(basis, plan, T=512, threads=256, ring=2):
     fp.w = float(basis.W[0])
     fp.nqp = int(basis.nqp)
     fp.p = p
+    # coordinates all 0 or within [2^-60, 2^60]: the kernel's exact division
+    # needs no per-element exponent checks (csrc/skb_p1_fused.cu, P1Args::tame)
+    ap = p.abs()
+    fp.tame = int(bool(((ap == 0) | ((ap >= 2.0 ** -60) & (ap <= 2.0 ** 60))).all()))
     fp.smem = int(_lib.lib().skb_p1_fused_smem_bytes(T, ring, fp.rec_cap, fp.vcap))
     if fp.smem > 227 * 1024:
         raise FusedPlanTooBig("fused plan: tile does not fit in shared memory "
@@ -258,7 +283,7 @@ class FusedPlanTooBig(RuntimeError):
     pass
 
 
-def build_auto(basis, plan, T=512, threads=256, ring=4):
+def build_auto(basis, plan, T=512, threads=480, ring=4):
     """Build with the requested tile, halving it while the tile's record ring
     and coordinates do not fit in shared memory (irregular meshes whose tiles
     touch many vertices).  Returns None if even the smallest tile is too big:
@@ -278,11 +303,11 @@ def run(fp, data, stream):
     lib = _lib.lib()
     code = lib.skb_p1tet_laplace_fused(
         fp.p.data_ptr(), fp.p.shape[1], fp.rec.data_ptr(), fp.rec_start.data_ptr(), fp.ntiles,
-        fp.T, fp.threads, fp.ring, fp.rec_cap, fp.vcap, C.c_double(fp.w), fp.nqp,
+        fp.T, fp.threads, fp.ring, fp.rec_cap, fp.vcap, fp.tame, C.c_double(fp.w), fp.nqp,
         data.data_ptr(), fp.scratch.data_ptr(), stream)
     _lib.check(code, "skb_p1tet_laplace_fused")
     code = lib.skb_p1_combine(fp.scratch.data_ptr(), fp.sptr.data_ptr(), fp.gslot.data_ptr(),
-                              fp.nshared, data.data_ptr(), stream)
+                              fp.gslot2.data_ptr(), fp.nshared, data.data_ptr(), stream)
     _lib.check(code, "skb_p1_combine")
 
 
@@ -290,9 +315,8 @@ def stats(fp):
     """Bytes the fused step moves (for DESIGN.md / the roofline discussion)."""
     b = {
         "records": fp.rec_bytes, "p_gather_min": fp.nverts_tiles * 24,
-        "direct_out": (fp.nnz - fp.nshared) * 8, "scratch_w": fp.nscratch * 8,
-        "scratch_r": fp.nscratch * 8, "sptr_gslot": fp.nshared * 8,
-        "combine_out": fp.nshared * 8,
+        "csr_out": fp.nnz * 8, "scratch_w": fp.nscratch * 8,
+        "scratch_r": fp.nscratch * 8, "sptr_gslot": fp.nshared * 12,
     }
     b["total"] = sum(b.values())
     b["per_element"] = b["total"] / max(fp.nel, 1)

@@ -185,8 +185,8 @@ def test_quadrature_mismatch_errors():
         laplace.assemble(b1, b2)
 
 
-@pytest.mark.parametrize("tile,threads,ring", [(512, 256, 4), (512, 512, 5), (512, 128, 4),
-                                               (256, 128, 5), (256, 256, 4), (768, 256, 4)])
+@pytest.mark.parametrize("tile,threads,ring", [(512, 256, 4), (512, 480, 5), (512, 128, 4),
+                                               (256, 128, 5), (256, 256, 4), (768, 224, 4)])
 def test_fused_p1_path(tile, threads, ring):
     """Warm re-assembly goes through the fused kernel (csrc/skb_p1_fused.cu):
     same plan (indptr/indices bit-exact), values within rtol 1e-12 of the
@@ -222,6 +222,17 @@ def test_fused_p1_path(tile, threads, ring):
         np.testing.assert_allclose(A.data, Ao.data, rtol=RTOL, atol=RTOL * np.abs(Ao.data).max())
         fp = b._plans[("fused", laplace._plan_key(b, None, {}))]
         assert fp.ntiles == -(-m.nelements // fp.T) and fp.nshared > 0 and fp.T <= tile
+        # coordinates outside [2^-60, 2^60]: the kernel must take plain IEEE division
+        ms_ = fem.MeshTet(m.p * 2.0 ** -80, m.t)
+        bw = fem.Basis(ms_, fem.ElementTetP1())
+        laplace.assemble(bw)
+        Aw = laplace.assemble(bw)
+        assert b._plans[("fused", laplace._plan_key(b, None, {}))].tame == 1
+        assert bw._plans[("fused", laplace._plan_key(bw, None, {}))].tame == 0
+        Awo = O.assemble_bilinear(O.laplace, O.cell_basis(mesh_of(dict(p=ms_.p, t=ms_.t), "tet"),
+                                                          O.element("tet_p1")))
+        assert np.array_equal(Aw.indices, Awo.indices)
+        np.testing.assert_allclose(Aw.data, Awo.data, rtol=RTOL, atol=RTOL * np.abs(Awo.data).max())
         # element subset
         sub = np.arange(0, m.nelements, 3)
         bs = fem.Basis(m, fem.ElementTetP1(), elements=sub)
@@ -233,4 +244,4 @@ def test_fused_p1_path(tile, threads, ring):
         np.testing.assert_allclose(As.data, Aso.data, rtol=RTOL,
                                    atol=RTOL * np.abs(Aso.data).max())
     finally:
-        F.set_options(fused=True, fused_tile=512, fused_threads=256, fused_ring=4)
+        F.set_options(fused=True, fused_tile=512, fused_threads=480, fused_ring=4)
