@@ -1,0 +1,71 @@
+"""Turn the ncu artefacts a gpurun call left in gpurun_out/ into the tracked
+summaries under profiles/ (round-1 naming).  Usage:
+    python tools/summarize_profiles.py r1
+"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+os.makedirs(P, exist_ok=True)
+
+# 1. launch list -> per-kernel average duration and share of the step
+src = os.path.join(G, "launches_%s.csv" % tag)
+if os.path.exists(src):
+    lines = [l for l in open(src) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        agg.setdefault(row["Kernel Name"], []).append(float(row["Metric Value"].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    with open(os.path.join(P, "%s_launches.md" % tag), "w") as f:
+        f.write("# ncu launch list (%s): `ncu --metrics gpu__time_duration.sum --clock-control none`\n\n"
+                "Command: `python bench.py --steps 5 --warmup 3 --no-cpu --no-graph` (1 GPU). "
+                "Durations are cold-cache and serialised under ncu; compare shares.\n\n"
+                "| kernel | launches | avg us | share of listed time |\n|---|---|---|---|\n" % tag)
+        for k, v in agg.items():
+            f.write("| `%s` | %d | %.1f | %.1f %% |\n" % (k[:90], len(v), sum(v) / len(v) / 1e3,
+                                                         100 * sum(v) / tot))
+    print("wrote launches")
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__block_size", "launch__grid_size", "launch__shared_mem_per_block_dynamic",
+        "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
+        "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
+        "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_wait",
+        "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle",
+        "smsp__pcsamp_warps_issue_stalled_mio_throttle", "smsp__pcsamp_warps_issue_stalled_not_selected",
+        "smsp__pcsamp_warps_issue_stalled_selected", "smsp__pcsamp_sample_buffer_full"]
+for name in ("fused", "combine"):
+    rep = os.path.join(G, "prof_%s_%s.ncu-rep" % (tag, name))
+    if not os.path.exists(rep):
+        continue
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+    with open(os.path.join(P, "%s_ncu_%s.md" % (tag, name)), "w") as f:
+        f.write("# ncu --set full --clock-control none: `%s`\n\n" % d.get("Kernel Name", ("?",))[0])
+        f.write("Command: `python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-graph` "
+                "(BASELINE configs[1], 6.0 M P1 tets, 1 GPU). One launch.\n\n| metric | value | unit |\n|---|---|---|\n")
+        for w in WANT:
+            if w in d:
+                f.write("| %s | %s | %s |\n" % (w, d[w][0], d[w][1]))
+        try:
+            rd = float(d["dram__bytes_read.sum"][0]); wr = float(d["dram__bytes_write.sum"][0])
+            f.write("\nDRAM traffic of this launch: %.1f MB (read %.1f + write %.1f).\n" % (rd + wr, rd, wr))
+        except Exception:
+            pass
+    print("wrote", name)
