@@ -156,36 +156,53 @@ def run_gpu(args):
     _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads,
                       fused_ring=args.ring)
     cells = args.cells
-    x = np.linspace(0, 1, cells + 1)
+    da = None
     if world == 1:
-        z = x
-    else:  # weak scaling: rank r owns the slab z in [r, r+1]
-        z = np.linspace(rank, rank + 1, cells + 1)
-    m = fem.MeshTet.init_tensor(x, x, z)
+        x = np.linspace(0, 1, cells + 1)
+        m = fem.MeshTet.init_tensor(x, x, x)
+    else:
+        # weak scaling: rank r assembles the z-slab [r, r+1] (cells^3 cells) of a
+        # mesh `world` slabs tall; interface rows go to their owner over NCCL
+        from skfem_b200.distributed import DistributedAssembler, slab_mesh_tet
+        m, l2g, Nglob, ranges = slab_mesh_tet(cells, cells, rank, world)
     basis = fem.Basis(m, fem.ElementTetP1())
     nel = m.nelements
 
     # cold assembly: builds and caches the plan (not part of the warm step)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    A = laplace.assemble_device(basis)
+    if world == 1:
+        A = laplace.assemble_device(basis)
+    else:
+        da = DistributedAssembler(laplace, basis, l2g, Nglob, ranges)
+        A = da.assemble()
     torch.cuda.synchronize()
     cold_ms = 1e3 * (time.perf_counter() - t0)
     nnz = A.nnz
+    if world > 1:
+        tn = torch.tensor([nnz], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tn)
+        nnz_total = int(tn.item())
+    else:
+        nnz_total = nnz
 
-    out = torch.empty(nnz, dtype=torch.float64, device="cuda")
     if args.debug_flags:
         _lib.lib().skb_debug_flags(args.debug_flags)   # profiling only: results invalid
 
-    def step_eager():
-        return laplace.assemble_device(basis, out=out)
+    if world == 1:
+        out = torch.empty(nnz, dtype=torch.float64, device="cuda")
+
+        def step_eager():
+            return laplace.assemble_device(basis, out=out)
+    else:
+        step_eager = da.assemble     # local fused assembly + interface exchange + ordered add
 
     for _ in range(2):
         step_eager()                 # builds the fused tile plan on the first warm call
     torch.cuda.synchronize()
     launches_per_step = None
     graph = None
-    if not args.no_graph:
+    if not args.no_graph and world == 1:
         # the warm step is launch bound from Python: capture it once, replay it
         _lib.lib().skb_launch_count(1)
         graph = torch.cuda.CUDAGraph()
@@ -233,7 +250,11 @@ def run_gpu(args):
         def e2e_step():
             mm = fem.MeshTet(p_host, t_host)
             bb = fem.Basis(mm, fem.ElementTetP1())
-            return laplace.assemble(bb)
+            if world == 1:
+                return laplace.assemble(bb)
+            # every rank: its slab in, its row block of the global matrix out
+            return DistributedAssembler(laplace, bb, l2g, Nglob, ranges).assemble() \
+                .to_scipy_block()
         for _ in range(2):
             Ah = e2e_step()
         if world > 1:
@@ -276,10 +297,17 @@ def run_gpu(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "nnz_per_s": nnz * world / (ms_step * 1e-3),
-        "config": {"workload": "MeshTet.init_tensor {}^3 pts ElementTetP1 laplace "
-                               "(BASELINE configs[1]) warm re-assembly into CSR".format(cells + 1),
+        "nnz_per_s": nnz_total / (ms_step * 1e-3),
+        "config": {"workload": ("MeshTet.init_tensor {}^3 pts ElementTetP1 laplace "
+                                "(BASELINE configs[1]) warm re-assembly into CSR".format(cells + 1)
+                                if world == 1 else
+                                "MeshTet.init_tensor z-slab of {0}^3 cells per GPU, {1} slabs, "
+                                "ElementTetP1 laplace, warm re-assembly into a row-partitioned "
+                                "CSR, interface rows exchanged over NCCL".format(cells, world)),
                    "elements_per_gpu": nel, "dofs_per_gpu": basis.N, "nnz_per_gpu": nnz,
+                   "nnz_total": nnz_total,
+                   "interface_bytes_sent_rank0": (da.exchange.bytes_per_exchange
+                                                  if da is not None else 0),
                    "l2": "no flush: per-step working set (t, local data, plan) exceeds the 126 MB L2",
                    "cold_plan_build_ms": cold_ms,
                    "path": "fused" if fused_stats else "generic", "fused_plan": fused_stats},

@@ -1,0 +1,199 @@
+"""Multi-GPU assembly: one process per GPU, element-partitioned, row-partitioned
+result, interface rows exchanged over NCCL (NVLink 5 / NVSwitch).
+
+The reference's only distributed route is host MPI + PETSc: METIS partition ->
+per-rank sub-mesh + local->global DOF map (``Dofs.decompose``,
+skfem/assembly/dofs.py:358-511) -> every rank runs the serial assembler ->
+PETSc ``MATIS -> mpiaij`` adds the interface rows across ranks
+(skfem/assembly/form/coo_data.py:118-172).  The same decomposition here:
+
+* every rank assembles its own elements with the single-GPU engine into a
+  *local* CSR (local DOF numbering, value-dependent pattern);
+* ``l2g`` maps local DOFs to global ones (the reference's ``_globnums``);
+  global rows are owned in contiguous ranges ``[ranges[k], ranges[k+1])``;
+* plan (once): the (row, col) keys of slots whose row another rank owns are
+  sent to that owner; the owner merges them with its own keys (sorted unique)
+  into its final row block and remembers where every incoming value lands.
+  A slot exists iff some rank has a non-zero contribution - the union of the
+  ranks' value-dependent patterns, i.e. the reference's pattern;
+* numeric (every assembly): pack the off-rank values, one all-to-all-v,
+  then add the received segments in source-rank order.  Inside one segment all
+  target slots are distinct, so the result is deterministic.
+
+Only neighbours exchange data for slab-like partitions; the payload is one
+vertex layer (a few MB), so the exchange is latency- not bandwidth-bound and is
+left to NCCL point-to-point (no data-path collective beyond it).
+
+The exchange logic is device agnostic (torch CPU tensors + gloo work too):
+tests/test_distributed_cpu.py drives it with world_size 2 on CPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def balanced_ranges(n, world):
+    """Contiguous ownership ranges of n rows over `world` ranks."""
+    base, extra = divmod(int(n), int(world))
+    ends = np.cumsum([base + (1 if k < extra else 0) for k in range(world)])
+    return np.concatenate([[0], ends]).astype(np.int64)
+
+
+def all_to_all_v(send, send_counts, recv_counts, group=None):
+    """Variable all-to-all on the current backend via grouped point-to-point
+    (NCCL: one ncclGroup of send/recv; gloo: the same calls on CPU tensors).
+    `send` is laid out destination-major."""
+    torch = _torch()
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+    so = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64)
+    ro = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
+    ops = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if recv_counts[peer]:
+            ops.append(dist.P2POp(dist.irecv, recv[ro[peer]:ro[peer + 1]], peer, group))
+        if send_counts[peer]:
+            ops.append(dist.P2POp(dist.isend, send[so[peer]:so[peer + 1]].contiguous(), peer,
+                                  group))
+    if send_counts[rank]:
+        recv[ro[rank]:ro[rank + 1]] = send[so[rank]:so[rank + 1]]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return recv
+
+
+class InterfaceExchange:
+    """Plan + numeric phase of the interface-row reduction for one local CSR
+    pattern.  ``grow``/``gcol``: global row / column of every local CSR slot
+    (int64 tensors on the compute device)."""
+
+    def __init__(self, grow, gcol, ranges, ncols, group=None):
+        torch = _torch()
+        import torch.distributed as dist
+        self.group = group
+        self.rank = rank = dist.get_rank(group)
+        self.world = world = dist.get_world_size(group)
+        self.ranges = np.asarray(ranges, dtype=np.int64)
+        self.ncols = int(ncols)
+        dev = grow.device
+        ends = torch.as_tensor(self.ranges[1:], device=dev)
+        owner = torch.searchsorted(ends, grow, right=True)
+        key = grow * self.ncols + gcol
+        # destination-major, key-sorted send order (deterministic)
+        order = torch.argsort(owner * (int(self.ranges[-1]) * self.ncols + 1) + key)
+        owner_s = owner[order]
+        counts = torch.bincount(owner_s, minlength=world)[:world]
+        self.send_counts = [int(c) for c in counts.cpu()]
+        self.send_order = order
+        # exchange counts, then keys
+        cnt_t = torch.as_tensor(self.send_counts, dtype=torch.int64, device=dev)
+        recv_cnt = all_to_all_v(cnt_t, [1] * world, [1] * world, group)
+        self.recv_counts = [int(c) for c in recv_cnt.cpu()]
+        recv_keys = all_to_all_v(key[order], self.send_counts, self.recv_counts, group)
+        # my final row block: sorted unique of everything addressed to me
+        final = torch.unique(recv_keys, sorted=True)
+        self.pos_recv = torch.searchsorted(final, recv_keys)
+        r0, r1 = int(self.ranges[rank]), int(self.ranges[rank + 1])
+        rows = final // self.ncols - r0
+        self.nrows = r1 - r0
+        self.row0 = r0
+        self.nnz = int(final.shape[0])
+        self.indices = (final - (rows + r0) * self.ncols)
+        rowcount = torch.bincount(rows, minlength=self.nrows)[:self.nrows]
+        self.indptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev),
+                                 torch.cumsum(rowcount, 0)])
+        self.ro = np.concatenate([[0], np.cumsum(self.recv_counts)]).astype(np.int64)
+        self.bytes_per_exchange = 8 * (sum(self.send_counts) - self.send_counts[rank])
+
+    def reduce(self, local_vals):
+        """Values of my row block from every rank's local values."""
+        torch = _torch()
+        packed = local_vals[self.send_order]                     # pack (gather)
+        recv = all_to_all_v(packed, self.send_counts, self.recv_counts, self.group)
+        data = torch.zeros(self.nnz, dtype=local_vals.dtype, device=local_vals.device)
+        for src in range(self.world):                            # fixed order: deterministic
+            a, b = int(self.ro[src]), int(self.ro[src + 1])
+            if b > a:
+                data.index_add_(0, self.pos_recv[a:b], recv[a:b])  # distinct targets per source
+        return data
+
+
+class DistributedCSR:
+    """Row block of the global matrix owned by this rank: rows
+    ``[row0, row0+nrows)``, global column indices."""
+
+    def __init__(self, indptr, indices, data, row0, shape):
+        self.indptr, self.indices, self.data = indptr, indices, data
+        self.row0, self.shape = int(row0), tuple(shape)
+
+    @property
+    def nnz(self):
+        return int(self.data.shape[0])
+
+    def to_scipy_block(self):
+        from scipy.sparse import csr_matrix
+        nrows = int(self.indptr.shape[0]) - 1
+        return csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
+                           self.indptr.cpu().numpy()), shape=(nrows, self.shape[1]))
+
+
+class DistributedAssembler:
+    """``form`` assembled over a rank-local basis into a row-partitioned CSR.
+
+    basis   rank-local CellBasis (sub-mesh with local DOF numbering)
+    l2g     int64 array, local DOF -> global DOF (the reference's _globnums)
+    N       global number of DOFs
+    ranges  ownership ranges of global rows (len world+1); default balanced
+    """
+
+    def __init__(self, form, basis, l2g, N, ranges=None, group=None):
+        import torch.distributed as dist
+        self.form, self.basis, self.N, self.group = form, basis, int(N), group
+        self.world = dist.get_world_size(group)
+        self.ranges = balanced_ranges(N, self.world) if ranges is None else np.asarray(ranges)
+        self.l2g_host = np.asarray(l2g, dtype=np.int64)
+        self.exchange = None
+
+    def assemble(self):
+        torch = _torch()
+        A = self.form.assemble_device(self.basis)            # local CSR, local numbering
+        if self.exchange is None:                             # plan: once per pattern
+            dev = A.data.device
+            l2g = torch.as_tensor(self.l2g_host, device=dev)
+            counts = (A.indptr[1:] - A.indptr[:-1]).long()
+            lrow = torch.repeat_interleave(torch.arange(A.shape[0], device=dev), counts)
+            self.exchange = InterfaceExchange(l2g[lrow], l2g[A.indices.long()], self.ranges,
+                                              self.N, self.group)
+        ex = self.exchange
+        data = ex.reduce(A.data)
+        return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
+
+
+def slab_mesh_tet(cells_xy, cells_z, rank, world, mesh_cls=None):
+    """Rank-local z-slab of a (cells_xy x cells_xy x cells_z*world) init_tensor
+    tetrahedral mesh of the unit-spaced box, its local->global vertex map and
+    the global vertex count.  Vertex numbering of ``MeshTet.init_tensor`` is
+    z-major (index = iy + npy*ix + npy*npx*iz), so a z-slab owns a contiguous
+    range of global vertices and shares exactly one vertex layer with each
+    neighbour."""
+    from .mesh import MeshTet
+    mesh_cls = MeshTet if mesh_cls is None else mesh_cls
+    x = np.linspace(0, 1, cells_xy + 1)
+    z = np.linspace(rank * 1.0, rank + 1.0, cells_z + 1)
+    m = mesh_cls.init_tensor(x, x, z)
+    layer = (cells_xy + 1) ** 2
+    l2g = np.arange(m.p.shape[1], dtype=np.int64) + rank * layer * cells_z
+    N = layer * (cells_z * world + 1)
+    # rows of a slab's top layer belong to the next rank (it owns z >= its base)
+    ranges = np.array([k * layer * cells_z for k in range(world)] + [N], dtype=np.int64)
+    return m, l2g, N, ranges
