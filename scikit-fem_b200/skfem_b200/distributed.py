@@ -114,6 +114,47 @@ class InterfaceExchange:
                                  torch.cumsum(rowcount, 0)])
         self.ro = np.concatenate([[0], np.cumsum(self.recv_counts)]).astype(np.int64)
         self.bytes_per_exchange = 8 * (sum(self.send_counts) - self.send_counts[rank])
+        # ---- direct-write layout for the fused kernel --------------------------------
+        # The kernel can write every local CSR slot straight to its destination:
+        # out = [ my final row block (nnz) | send buffer, destination-major ].
+        # slot_map[local slot] = index in `out`.
+        so = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
+        nloc = int(key.shape[0])
+        a_self, b_self = int(so[rank]), int(so[rank + 1])
+        own_slots = order[a_self:b_self]
+        ra, rb = int(self.ro[rank]), int(self.ro[rank + 1])
+        slot_map = torch.empty(nloc, dtype=torch.int64, device=dev)
+        slot_map[own_slots] = self.pos_recv[ra:rb]               # own slots -> final positions
+        remote = torch.cat([order[:a_self], order[b_self:]])     # destination-major
+        self.nsend = int(remote.shape[0])
+        slot_map[remote] = self.nnz + torch.arange(self.nsend, device=dev)
+        self.slot_map = slot_map
+        self.send_counts_remote = list(self.send_counts)
+        self.send_counts_remote[rank] = 0
+        self.recv_counts_remote = list(self.recv_counts)
+        self.recv_counts_remote[rank] = 0
+        self.pos_recv_remote = torch.cat([self.pos_recv[:ra], self.pos_recv[rb:]])
+        self.ro_remote = np.concatenate([[0], np.cumsum(self.recv_counts_remote)]).astype(np.int64)
+        # final slots nobody on this rank writes (received-only) must start at zero
+        written = torch.zeros(self.nnz, dtype=torch.bool, device=dev)
+        written[self.pos_recv[ra:rb]] = True
+        self.unwritten = torch.nonzero(~written).flatten()
+
+    def finish(self, out):
+        """Numeric phase when the kernel wrote `out` through ``slot_map``:
+        exchange the send-buffer tail and add the received segments (source-rank
+        order) into the row block at the head of `out`.  Returns the block."""
+        data = out[:self.nnz]
+        if self.unwritten.numel():
+            data[self.unwritten] = 0.0
+        if self.world > 1:
+            recv = all_to_all_v(out[self.nnz:], self.send_counts_remote, self.recv_counts_remote,
+                                self.group)
+            for src in range(self.world):
+                a, b = int(self.ro_remote[src]), int(self.ro_remote[src + 1])
+                if b > a:
+                    data.index_add_(0, self.pos_recv_remote[a:b], recv[a:b])
+        return data
 
     def reduce(self, local_vals):
         """Values of my row block from every rank's local values."""
@@ -166,16 +207,22 @@ class DistributedAssembler:
 
     def assemble(self):
         torch = _torch()
-        A = self.form.assemble_device(self.basis)            # local CSR, local numbering
-        if self.exchange is None:                             # plan: once per pattern
+        if self.exchange is None:                             # cold: local plan + exchange plan
+            A = self.form.assemble_device(self.basis)         # local CSR, local numbering
             dev = A.data.device
             l2g = torch.as_tensor(self.l2g_host, device=dev)
             counts = (A.indptr[1:] - A.indptr[:-1]).long()
             lrow = torch.repeat_interleave(torch.arange(A.shape[0], device=dev), counts)
-            self.exchange = InterfaceExchange(l2g[lrow], l2g[A.indices.long()], self.ranges,
-                                              self.N, self.group)
+            self.exchange = ex = InterfaceExchange(l2g[lrow], l2g[A.indices.long()],
+                                                   self.ranges, self.N, self.group)
+            data = ex.reduce(A.data)
+            return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
+        # warm: the kernels write every value straight to its place in
+        # [row block | send buffer]; then one exchange + ordered add
         ex = self.exchange
-        data = ex.reduce(A.data)
+        out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64, device=ex.slot_map.device)
+        self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
+        data = ex.finish(out)
         return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
 
 

@@ -393,18 +393,24 @@ class BilinearForm(Form):
         return (id(self.form) if self.native is None else self.native[:3],
                 id(vbasis) if vbasis is not None else None)
 
-    def assemble_device(self, ubasis, vbasis=None, out=None, **kwargs) -> DeviceCSR:
+    def assemble_device(self, ubasis, vbasis=None, out=None, slot_map=None,
+                        **kwargs) -> DeviceCSR:
         """Assemble into a device-resident CSR (no host transfer).
 
         ``out``: optional float64 device tensor of length nnz that receives
         the values (warm calls only - the plan must exist).  With ``out`` the
         call allocates nothing and can be captured in a CUDA graph, which is
-        how re-assembly loops (time stepping, Newton) should drive it."""
+        how re-assembly loops (time stepping, Newton) should drive it.
+        ``slot_map`` (with ``out``): int64 tensor, CSR slot -> index in ``out``;
+        the kernels then scatter the values straight to those positions (used by
+        the multi-GPU path to write [row block | send buffer] in one pass)."""
         assert self.form is not None
         torch = _torch()
         vb = ubasis if vbasis is None else vbasis
         key = self._plan_key(ubasis, vbasis, kwargs)
         plan = ubasis._plans.get(key) if key is not None else None
+        if slot_map is not None and (out is None or plan is None):
+            raise ValueError("slot_map= needs out= and an existing plan")
         # warm re-assembly of a fusable form: geometry -> CSR values in one
         # pass (csrc/skb_p1_fused.cu); the tile plan is built on the first
         # warm call from the pattern the cold call established
@@ -412,12 +418,13 @@ class BilinearForm(Form):
                 and ubasis.nelems > 0 and plan.nnz > 0):
             from . import fused
             if fused.applicable(ubasis, self):
-                fkey = ("fused", key)
+                fkey = ("fused", key) if slot_map is None else ("fused-mapped", key,
+                                                                id(slot_map))
                 fp = ubasis._plans.get(fkey, False)
                 if fp is False:
                     fp = fused.build_auto(ubasis, plan, T=fused_tile(),
                                           threads=int(_CONFIG["fused_threads"]),
-                                          ring=int(_CONFIG["fused_ring"]))
+                                          ring=int(_CONFIG["fused_ring"]), slot_map=slot_map)
                     ubasis._plans[fkey] = fp      # None: tiles too big, stay generic
                 if fp is not None:
                     data = out if out is not None else torch.empty(
@@ -432,12 +439,15 @@ class BilinearForm(Form):
                               (vb.N, ubasis.N), local, drop_zeros=True)
             if key is not None:
                 ubasis._plans[key] = plan
-        data = out if out is not None else torch.empty(plan.nnz, dtype=torch.float64,
-                                                       device=local.device)
+        data = out if (out is not None and slot_map is None) else torch.empty(
+            plan.nnz, dtype=torch.float64, device=local.device)
         code = _lib.lib().skb_csr_reduce(local.data_ptr(), plan.perm.data_ptr(),
                                          plan.segptr.data_ptr(), plan.nnz, data.data_ptr(),
                                          _stream())
         _lib.check(code, "skb_csr_reduce")
+        if slot_map is not None:        # generic path: scatter through the map afterwards
+            out[slot_map] = data
+            data = out
         return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
 
     def assemble(self, ubasis, vbasis=None, **kwargs):

@@ -67,7 +67,9 @@ def applicable(basis, form):
     return bool(np.all(W == W[0]))
 
 
-def build(basis, plan, T=512, threads=480, ring=4):
+def build(basis, plan, T=512, threads=480, ring=4, slot_map=None):
+    """``slot_map`` (optional int64 tensor, CSR slot -> output index): targets
+    written by the kernels are remapped through it (multi-GPU direct write)."""
     torch = _torch()
     d = basis._dev()
     dev = d["device"]
@@ -195,19 +197,23 @@ def build(basis, plan, T=512, threads=480, ring=4):
     grp = torch.repeat_interleave(arange(int(ug.shape[0])), gcnt)
     spos = gstart[grp] + (ts_idx - gfirst[grp])
     NONE = 0xFFFFFFFF
+
+    def tgt(slots):                      # where a CSR slot's value is written
+        return slots if slot_map is None else slot_map[slots]
     meta = torch.empty(nts, dtype=i64, device=dev)
-    meta[order2] = torch.where(shared[grp], spos | 0x80000000, g_sorted)
+    meta[order2] = torch.where(shared[grp], spos | 0x80000000, tgt(g_sorted))
     # mirror target: written by the tile only for exclusive off-diagonal slots
     # (shared ones are mirrored by skb_p1_combine)
     mir_sorted = mirror[g_sorted]
     meta2 = torch.empty(nts, dtype=i64, device=dev)
     meta2[order2] = torch.where(shared[grp] | (mir_sorted == g_sorted),
-                                torch.full_like(g_sorted, NONE), mir_sorted)
+                                torch.full_like(g_sorted, NONE), tgt(mir_sorted))
     sh = torch.nonzero(shared).flatten()
     fp.nshared = int(sh.shape[0])
     fp.nscratch = int(gsz.sum())
-    fp.gslot = ug[sh].to(torch.int32).contiguous()
-    fp.gslot2 = mirror[ug[sh]].to(torch.int32).contiguous()
+    # diagonal slots mirror onto themselves: keep gslot2 == gslot after mapping
+    fp.gslot = tgt(ug[sh]).to(torch.int32).contiguous()
+    fp.gslot2 = tgt(mirror[ug[sh]]).to(torch.int32).contiguous()
     fp.sptr = torch.cat([gstart[sh], torch.tensor([fp.nscratch], device=dev, dtype=i64)]
                         ).to(torch.int32).contiguous()
     fp.scratch = torch.empty(max(fp.nscratch, 1), dtype=torch.float64, device=dev)
@@ -283,16 +289,16 @@ class FusedPlanTooBig(RuntimeError):
     pass
 
 
-def build_auto(basis, plan, T=512, threads=480, ring=4):
+def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None):
     """Build with the requested tile, halving it while the tile's record ring
     and coordinates do not fit in shared memory (irregular meshes whose tiles
     touch many vertices).  Returns None if even the smallest tile is too big:
     the caller then stays on the generic path."""
-    options = [(T, threads)] + [c for c in ((512, 256), (256, 256), (256, 128))
+    options = [(T, threads)] + [c for c in ((512, 256), (256, 256), (256, 128), (128, 96))
                                 if c[0] < T]
     for tile, thr in options:
         try:
-            return build(basis, plan, T=tile, threads=thr, ring=ring)
+            return build(basis, plan, T=tile, threads=thr, ring=ring, slot_map=slot_map)
         except FusedPlanTooBig:
             continue
     return None

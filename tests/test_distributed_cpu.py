@@ -47,6 +47,11 @@ def _worker(rank, world, port, cxy, cz, out):
         d1 = ex.reduce(torch.as_tensor(Aloc.data))
         d2 = ex.reduce(torch.as_tensor(Aloc.data))
         assert torch.equal(d1, d2)                                   # deterministic
+        # direct-write layout used by the fused kernel: [row block | send buffer]
+        out_ = torch.full((ex.nnz + ex.nsend,), float("nan"), dtype=torch.float64)
+        out_[ex.slot_map] = torch.as_tensor(Aloc.data)
+        d3 = ex.finish(out_)
+        np.testing.assert_allclose(d3.numpy(), d1.numpy(), rtol=1e-15, atol=0)
         Ag = O.assemble_bilinear(O.laplace, O.cell_basis(_global_mesh(cxy, cz, world),
                                                          O.element("tet_p1")))
         blk = Ag[ex.row0:ex.row0 + ex.nrows]
