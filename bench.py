@@ -174,7 +174,7 @@ def run_gpu(args):
     if world == 1:
         A = laplace.assemble_device(basis)
     else:
-        da = DistributedAssembler(laplace, basis, l2g, Nglob, ranges)
+        da = DistributedAssembler(laplace, basis, l2g, Nglob, ranges, reuse_buffers=True)
         A = da.assemble()
     torch.cuda.synchronize()
     cold_ms = 1e3 * (time.perf_counter() - t0)
@@ -230,6 +230,8 @@ def run_gpu(args):
     launches = int(_lib.lib().skb_launch_count(0))
     if graph is not None:            # replays launch the captured kernels, not the C API
         launches = launches_per_step * args.steps
+    elif da is not None:             # the assembler replays its own graph: fused + combine
+        launches = 2 * args.steps
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:

@@ -53,6 +53,10 @@ def all_to_all_v(send, send_counts, recv_counts, group=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+    if dist.get_backend(group) == "nccl":        # one grouped ncclSend/ncclRecv
+        dist.all_to_all_single(recv, send.contiguous(), [int(c) for c in recv_counts],
+                               [int(c) for c in send_counts], group=group)
+        return recv
     so = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64)
     ro = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
     ops = []
@@ -197,9 +201,11 @@ class DistributedAssembler:
     ranges  ownership ranges of global rows (len world+1); default balanced
     """
 
-    def __init__(self, form, basis, l2g, N, ranges=None, group=None):
+    def __init__(self, form, basis, l2g, N, ranges=None, group=None, reuse_buffers=False):
         import torch.distributed as dist
         self.form, self.basis, self.N, self.group = form, basis, int(N), group
+        self.reuse_buffers = bool(reuse_buffers)
+        self._graph = self._out = None
         self.world = dist.get_world_size(group)
         self.ranges = balanced_ranges(N, self.world) if ranges is None else np.asarray(ranges)
         self.l2g_host = np.asarray(l2g, dtype=np.int64)
@@ -220,9 +226,24 @@ class DistributedAssembler:
         # warm: the kernels write every value straight to its place in
         # [row block | send buffer]; then one exchange + ordered add
         ex = self.exchange
-        out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64, device=ex.slot_map.device)
-        self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
-        data = ex.finish(out)
+        if not self.reuse_buffers:
+            out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64, device=ex.slot_map.device)
+            self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
+            data = ex.finish(out)
+            return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
+        # re-assembly loop mode: persistent output buffer, the local kernels are
+        # replayed from a CUDA graph, only the NCCL exchange is issued eagerly.
+        # The returned block aliases the internal buffer (overwritten next call).
+        if self._graph is None:
+            self._out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64,
+                                    device=ex.slot_map.device)
+            self.form.assemble_device(self.basis, out=self._out, slot_map=ex.slot_map)  # plan
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.form.assemble_device(self.basis, out=self._out, slot_map=ex.slot_map)
+        self._graph.replay()
+        data = ex.finish(self._out)
         return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
 
 
