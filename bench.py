@@ -294,6 +294,16 @@ def run_gpu(args):
             fused_stats["tile"], fused_stats["threads"], fused_stats["ring"] = v.T, v.threads, v.ring
     algo_bytes = 4 * 4 * nel + 8 * 3 * nverts + 8 * nnz   # t + p + CSR data (warm)
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+    # DRAM traffic per step from the committed `ncu --set full` captures (same workload/path)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f)
+        if (tr["cells"] == cells and tr["path"] == ("fused" if fused_stats else "generic")
+                and world == 1):
+            traffic = tr["dram_bytes_per_step"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -314,7 +324,7 @@ def run_gpu(args):
                    "cold_plan_build_ms": cold_ms,
                    "path": "fused" if fused_stats else "generic", "fused_plan": fused_stats},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": algo_bytes,
                      "note": "whole warm step (all kernels of the step) vs compulsory bytes "
                              "t + p + CSR data"},

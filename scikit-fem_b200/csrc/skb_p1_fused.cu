@@ -31,6 +31,7 @@
 //         position in a scratch array grouped by CSR slot.
 // skb_p1_combine then adds the per-tile partials of every shared slot in tile
 // order.  No float atomics anywhere: results are bit-reproducible.
+#include <cstdio>
 #include "skb_common.cuh"
 
 namespace skb {
@@ -52,7 +53,7 @@ struct P1Args {
 };
 
 struct RecHeader {              // 32 bytes at the start of every record
-  uint32_t nverts, ngroups, off_verts, off_grp, off_meta, off_ids, nslots, off_meta2;
+  uint32_t nverts, ngroups, off_verts, off_grp, off_meta, off_ids, off_fsel, off_meta2;
 };
 
 __device__ __forceinline__ constexpr int sym_index4(int a, int b) {  // a <= b
@@ -216,6 +217,10 @@ p1tet_laplace_fused_kernel(const P1Args a) {
   }
   __syncthreads();
 
+  // profiling aid (debug bit 2): cycles block 0 spends working vs at the barrier
+  const bool timing = (a.debug & 4) && blockIdx.x == 0 && lane == 0 &&
+                      (threadIdx.x == 0 || threadIdx.x == T_ELEMS);
+  long long t_work = 0, t_bar = 0, t_mark = timing ? clock64() : 0;
   for (int k = 0; k <= nk; ++k) {
     if (is_compute) {
       // ---- P1(k): local matrices of tile k -> vals[k & 1] ---------------------------
@@ -282,6 +287,7 @@ p1tet_laplace_fused_kernel(const P1Args a) {
         const uint32_t *grp = reinterpret_cast<const uint32_t *>(r + h->off_grp);
         const uint32_t *meta = reinterpret_cast<const uint32_t *>(r + h->off_meta);
         const uint32_t *meta2 = reinterpret_cast<const uint32_t *>(r + h->off_meta2);
+        const uint8_t *fsel = r + h->off_fsel;
         const uint16_t *ids = reinterpret_cast<const uint16_t *>(r + h->off_ids);
         // groups are sorted longest first, dealt round-robin to the reduce warps;
         // every list length is a multiple of 2 (padded with the staged zero)
@@ -292,6 +298,7 @@ p1tet_laplace_fused_kernel(const P1Args a) {
           const uint16_t *cb = ids + (size_t)(gi & 0xffffu) * 32 + lane;
           const uint32_t m = meta[g * 32 + lane];
           const uint32_t m2 = meta2[g * 32 + lane];
+          const int fs = fsel[g * 32 + lane];
           double acc = 0.0;
 #pragma unroll 2
           for (int c = 0; c < len; c += 2) {
@@ -300,6 +307,11 @@ p1tet_laplace_fused_kernel(const P1Args a) {
             acc = acc + a0;
             acc = acc + a1;
           }
+          // long lists are split over 2 or 4 adjacent lanes: fixed combination
+          // tree (l + l+1) + (l+2 + l+3), selected by the leader lane's fsel
+          const double t1 = acc + __shfl_down_sync(0xffffffffu, acc, 1);
+          const double t2 = t1 + __shfl_down_sync(0xffffffffu, t1, 2);
+          acc = fs == 0 ? acc : (fs == 1 ? t1 : t2);
           // the local matrix is bitwise symmetric: slot (r,c), r<c, and its
           // mirror (c,r) receive the same terms in the same order -> one sum
           if (m != 0xffffffffu) {
@@ -319,12 +331,17 @@ p1tet_laplace_fused_kernel(const P1Args a) {
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     }
+    if (timing) { const long long c = clock64(); t_work += c - t_mark; t_mark = c; }
     __syncthreads();  // vals[k&1] complete; record k-1 free; coords of tile k+1 visible
+    if (timing) { const long long c = clock64(); t_bar += c - t_mark; t_mark = c; }
     if (is_producer && k >= 1) {
       issue(k - 1 + NR);               // into the buffer tile k-1 vacated
       extent(k + NR);                  // its latency hides behind the next iteration
     }
   }
+  if (timing)
+    printf("[skb timing] block 0 %s warp: %d tiles, work %lld cycles, barrier wait %lld cycles\n",
+           threadIdx.x == 0 ? "compute" : "reduce ", nk, t_work, t_bar);
 }
 
 __global__ void __launch_bounds__(256)

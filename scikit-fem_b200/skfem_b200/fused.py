@@ -12,19 +12,25 @@ Elements are cut into tiles of ``T``.  Every tile gets one contiguous,
 16-byte aligned *record* (fetched by a single TMA bulk copy in the kernel):
 
     header  8 x uint32: nverts, ngroups, off_verts, off_grp, off_meta, off_ids,
-            nslots, bytes
+            off_fsel, off_meta2
     tl      T x 4 uint16  tile-local vertex ids (0xFFFF = padding element)
     verts   nverts int32  global vertex ids of the tile
-    grp     per group of 32 tile slots: uint32 (offset/32 into ids) | len << 16
-    meta    per tile slot: CSR slot, or 0x80000000 | scratch position
-            (0xFFFFFFFF for the unused lanes of the last group)
+    grp     per group of 32 lanes: uint32 (offset/32 into ids) | len << 16
+    meta    per lane: CSR slot, or 0x80000000 | scratch position
+            (0xFFFFFFFF for lanes that write nothing)
+    meta2   per lane: the mirror CSR slot (col,row) that receives the same sum
+            (0xFFFFFFFF on the diagonal / for shared slots)
+    fsel    per lane, one byte: log2 of the number of adjacent lanes whose
+            partial sums the leader lane combines (long lists are split)
     ids     sliced-ELL uint16 staging indices k(a,b)*T + e_local; entry c of
             lane l of a group sits at base + 32 c + l; short lists are padded
             with 10*T, the index of a staged 0.0
 
-A *tile slot* is a CSR slot touched by the tile.  Slots touched by one tile
-only are written straight to ``csr_data``; the others go to ``scratch``
-(grouped by CSR slot, tiles ascending) and are added by ``skb_p1_combine``.
+A *tile slot* is a canonical (row <= col) CSR slot touched by the tile; the
+Laplace local matrix is bitwise symmetric, so the mirror slot gets the same
+sum.  Slots touched by one tile only are written straight to ``csr_data``; the
+others go to ``scratch`` (grouped by CSR slot, tiles ascending) and are added
+by ``skb_p1_combine``.
 
 The preprocessing itself uses torch sort / unique / searchsorted (cold path,
 plumbing); the warm path runs only this package's kernels.
@@ -159,23 +165,34 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None):
     ts_tile = uniq // nnz
     ts_gslot = uniq - ts_tile * nnz
     kth = arange(ncontrib) - excl(cnt)[sinv]
-    # within a tile, order slots by decreasing contribution count (sliced ELL)
-    order3 = torch.argsort(ts_tile * 65536 + (65535 - cnt), stable=True)
+    # Long lists (diagonal slots collect ~24 terms) are split over F = 2 or 4
+    # adjacent lanes whose partial sums the kernel combines with shuffles in a
+    # fixed tree; this bounds the serial add chain of a lane to ~8 terms.
+    # Within a tile, slots are ordered F-major (keeps every F-block aligned to
+    # F lanes), then by decreasing chunk length (sliced ELL).
+    F = torch.where(cnt <= 8, 1, torch.where(cnt <= 16, 2, 4))
+    chunk = (cnt + F - 1) // F
+    fclass = torch.where(F == 4, 0, torch.where(F == 2, 1, 2))
+    order3 = torch.argsort((ts_tile * 4 + fclass) * 65536 + (65535 - chunk), stable=True)
     newpos = torch.empty(nts, dtype=i64, device=dev)
     newpos[order3] = arange(nts)
     ts_tile, ts_gslot, cnt = ts_tile[order3], ts_gslot[order3], cnt[order3]
+    F, chunk = F[order3], chunk[order3]
     tile_slot_start = torch.searchsorted(ts_tile, tile_ids)
     nslots_tile = tile_slot_start[1:] - tile_slot_start[:-1]
-    ngroups_tile = (nslots_tile + 31) // 32
+    Fcum = excl(F)
+    lane0 = Fcum - Fcum[tile_slot_start[:-1]][ts_tile]          # leader lane slot within tile
+    nlanes_tile = torch.zeros(ntiles, dtype=i64, device=dev).scatter_add_(0, ts_tile, F)
+    ngroups_tile = (nlanes_tile + 31) // 32
     tile_group_start = torch.cat([torch.zeros(1, dtype=i64, device=dev),
                                   torch.cumsum(ngroups_tile, 0)])
     ngroups = int(tile_group_start[-1])
     ts_idx = arange(nts)
-    j_in_tile = ts_idx - tile_slot_start[ts_tile]
-    grp_of_slot = tile_group_start[ts_tile] + j_in_tile // 32
-    lane_of_slot = j_in_tile % 32
+    j_in_tile = lane0                                            # leader position (meta, fsel)
+    grp_of_slot = tile_group_start[ts_tile] + lane0 // 32        # F-blocks never straddle groups
+    lane_of_slot = lane0 % 32
     grp_len = torch.zeros(ngroups, dtype=i64, device=dev)
-    grp_len.scatter_reduce_(0, grp_of_slot, cnt, reduce="amax", include_self=True)
+    grp_len.scatter_reduce_(0, grp_of_slot, chunk, reduce="amax", include_self=True)
     grp_len = (grp_len + 1) // 2 * 2                 # the kernel's P2 loop is unrolled by 2
     grp_tile = torch.repeat_interleave(arange(ntiles), ngroups_tile)
     gcum = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(grp_len * 32, 0)])
@@ -224,7 +241,8 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None):
     off_grp = off_verts + 4 * ((nverts_tile + 3) // 4 * 4)
     off_meta = off_grp + 16 * ((ngroups_tile + 3) // 4)
     off_meta2 = off_meta + 128 * ngroups_tile
-    off_ids = off_meta2 + 128 * ngroups_tile
+    off_fsel = off_meta2 + 128 * ngroups_tile        # one byte per lane: log2(F) of the leader
+    off_ids = off_fsel + 32 * ngroups_tile
     size = off_ids + 2 * nids_tile                   # multiple of 16
     rec_start = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(size, 0)])
     total = int(rec_start[-1])
@@ -233,7 +251,7 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None):
     buf16 = buf32.view(torch.int16)
     rs = rec_start[:-1]
     hdr = torch.stack([nverts_tile, ngroups_tile, torch.full_like(rs, off_verts), off_grp,
-                       off_meta, off_ids, nslots_tile, off_meta2], dim=1)
+                       off_meta, off_ids, off_fsel, off_meta2], dim=1)
     buf32[(rs // 4)[:, None] + arange(8)[None, :]] = hdr.to(torch.int32)
     # tl (padding elements of the last tile: 0xFFFF)
     pad = ntiles * T - nel
@@ -254,6 +272,10 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None):
     buf32[(rs[ts_tile] + off_meta[ts_tile]) // 4 + j_in_tile] = meta.to(torch.int32)
     buf32[((rs[grp_tile] + off_meta2[grp_tile]) // 4 + g_local * 32)[:, None] + lanes[None, :]] = -1
     buf32[(rs[ts_tile] + off_meta2[ts_tile]) // 4 + j_in_tile] = meta2.to(torch.int32)
+    # fsel: 0 -> the lane's own sum, 1 -> pair sum, 2 -> sum of four lanes (zero elsewhere)
+    buf8 = buf32.view(torch.uint8)
+    fsel = torch.where(F == 4, 2, torch.where(F == 2, 1, 0))
+    buf8[rs[ts_tile] + off_fsel[ts_tile] + j_in_tile] = fsel.to(torch.uint8)
     # ids: padding -> index of the staged zero, then the real contributions
     zero_idx = 10 * T
     tile_ids_start = excl(nids_tile)
@@ -264,7 +286,9 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None):
     s_new = newpos[sinv]
     g_of = grp_of_slot[s_new]
     t_of = grp_tile[g_of]
-    cpos = (rs[t_of] + off_ids[t_of]) // 2 + grp_base[g_of] + kth * 32 + lane_of_slot[s_new]
+    sub = kth // chunk[s_new]                        # which lane of the slot's F-block
+    cpos = ((rs[t_of] + off_ids[t_of]) // 2 + grp_base[g_of] + (kth - sub * chunk[s_new]) * 32
+            + lane_of_slot[s_new] + sub)
     buf16[cpos] = sid.to(torch.int16)
     fp.rec = buf32
     fp.rec_start = rec_start.contiguous()            # int64 == uint64 for the kernel

@@ -245,3 +245,32 @@ def test_fused_p1_path(tile, threads, ring):
                                    atol=RTOL * np.abs(Aso.data).max())
     finally:
         F.set_options(fused=True, fused_tile=512, fused_threads=480, fused_ring=4)
+
+
+def test_baseline_config2_full_size_properties():
+    """BASELINE configs[1] at full size (6.0 M P1 tets, 1 030 301 DOFs): the oracle
+    cannot be run on every box, so check size-independent properties: closed-form
+    nnz of the value-dependent pattern, symmetry, zero row sums (constants are
+    in the kernel), exact energy of a linear field, total load = volume, and
+    agreement of the cold (generic) and warm (fused) paths."""
+    from skfem_b200.models.poisson import laplace, unit_load, mass
+    n = 100
+    x = np.linspace(0, 1, n + 1)
+    b = fem.Basis(fem.MeshTet.init_tensor(x, x, x), fem.ElementTetP1())
+    assert b.N == (n + 1) ** 3 and b.nelems == 6 * n ** 3
+    A0 = laplace.assemble(b)            # cold: generic kernels + plan
+    A1 = laplace.assemble(b)            # warm: fused kernel
+    assert A0.nnz == (n + 1) ** 3 + 6 * n * (n + 1) ** 2 == 7150901
+    assert np.array_equal(A0.indptr, A1.indptr) and np.array_equal(A0.indices, A1.indices)
+    scale = np.abs(A0.data).max()
+    np.testing.assert_allclose(A1.data, A0.data, rtol=1e-12, atol=1e-12 * scale)
+    for A in (A0, A1):
+        assert abs(A - A.T).max() <= 1e-12 * scale
+        assert np.abs(A @ np.ones(b.N)).max() <= 1e-11 * scale
+        u = 2.0 * b.mesh.p[0] - 3.0 * b.mesh.p[1] + 0.5 * b.mesh.p[2]   # |grad u|^2 = 13.25
+        np.testing.assert_allclose(u @ (A @ u), 13.25, rtol=1e-11)
+    f = unit_load.assemble(b)
+    np.testing.assert_allclose(f.sum(), 1.0, rtol=1e-12)
+    M = mass.assemble(b)
+    np.testing.assert_allclose(M.sum(), 1.0, rtol=1e-11)
+    np.testing.assert_allclose(M @ np.ones(b.N), f, rtol=1e-10, atol=1e-18)

@@ -47,6 +47,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle",
         "smsp__pcsamp_warps_issue_stalled_mio_throttle", "smsp__pcsamp_warps_issue_stalled_not_selected",
         "smsp__pcsamp_warps_issue_stalled_selected", "smsp__pcsamp_sample_buffer_full"]
+dram_total = 0.0
 for name in ("fused", "combine"):
     rep = os.path.join(G, "prof_%s_%s.ncu-rep" % (tag, name))
     if not os.path.exists(rep):
@@ -66,6 +67,16 @@ for name in ("fused", "combine"):
         try:
             rd = float(d["dram__bytes_read.sum"][0]); wr = float(d["dram__bytes_write.sum"][0])
             f.write("\nDRAM traffic of this launch: %.1f MB (read %.1f + write %.1f).\n" % (rd + wr, rd, wr))
+            mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            dram_total += rd * mult.get(d["dram__bytes_read.sum"][1], 1e6) \
+                + wr * mult.get(d["dram__bytes_write.sum"][1], 1e6)
         except Exception:
             pass
     print("wrote", name)
+if dram_total:
+    with open(os.path.join(P, "traffic.json"), "w") as f:
+        json.dump({"cells": 100, "path": "fused", "dram_bytes_per_step": int(dram_total),
+                   "source": "profiles/%s_ncu_fused.md + %s_ncu_combine.md "
+                             "(dram__bytes_read.sum + dram__bytes_write.sum, one launch each)"
+                             % (tag, tag)}, f)
+    print("wrote traffic.json", dram_total)
