@@ -201,11 +201,14 @@ class DistributedAssembler:
     ranges  ownership ranges of global rows (len world+1); default balanced
     """
 
-    def __init__(self, form, basis, l2g, N, ranges=None, group=None, reuse_buffers=False):
+    def __init__(self, form, basis, l2g, N, ranges=None, group=None, reuse_buffers=False,
+                 graph_exchange=True):
         import torch.distributed as dist
         self.form, self.basis, self.N, self.group = form, basis, int(N), group
         self.reuse_buffers = bool(reuse_buffers)
-        self._graph = self._out = None
+        self.graph_exchange = bool(graph_exchange)
+        self._graph = self._out = self._data = None
+        self._graph_has_exchange = False
         self.world = dist.get_world_size(group)
         self.ranges = balanced_ranges(N, self.world) if ranges is None else np.asarray(ranges)
         self.l2g_host = np.asarray(l2g, dtype=np.int64)
@@ -238,12 +241,27 @@ class DistributedAssembler:
             self._out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64,
                                     device=ex.slot_map.device)
             self.form.assemble_device(self.basis, out=self._out, slot_map=ex.slot_map)  # plan
+            ex.finish(self._out)                                  # warms NCCL channels
             torch.cuda.synchronize()
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self.form.assemble_device(self.basis, out=self._out, slot_map=ex.slot_map)
+            self._graph_has_exchange = False
+            if self.graph_exchange:
+                # whole step (kernels + NCCL all-to-all + ordered adds) in one graph
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self.form.assemble_device(self.basis, out=self._out,
+                                                  slot_map=ex.slot_map)
+                        self._data = ex.finish(self._out)
+                    self._graph, self._graph_has_exchange = g, True
+                except Exception:                                  # NCCL capture unsupported
+                    torch.cuda.synchronize()
+                    self._graph = None
+            if self._graph is None:
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self.form.assemble_device(self.basis, out=self._out, slot_map=ex.slot_map)
         self._graph.replay()
-        data = ex.finish(self._out)
+        data = self._data if self._graph_has_exchange else ex.finish(self._out)
         return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
 
 
