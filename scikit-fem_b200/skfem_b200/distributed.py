@@ -144,12 +144,13 @@ class InterfaceExchange:
         written[self.pos_recv[ra:rb]] = True
         self.unwritten = torch.nonzero(~written).flatten()
 
-    def finish(self, out):
+    def finish(self, out, zero=True):
         """Numeric phase when the kernel wrote `out` through ``slot_map``:
         exchange the send-buffer tail and add the received segments (source-rank
-        order) into the row block at the head of `out`.  Returns the block."""
+        order) into the row block at the head of `out`.  Returns the block.
+        ``zero=False``: the caller already cleared the receive-only slots."""
         data = out[:self.nnz]
-        if self.unwritten.numel():
+        if zero and self.unwritten.numel():
             data[self.unwritten] = 0.0
         if self.world > 1:
             recv = all_to_all_v(out[self.nnz:], self.send_counts_remote, self.recv_counts_remote,
@@ -202,7 +203,9 @@ class DistributedAssembler:
     """
 
     def __init__(self, form, basis, l2g, N, ranges=None, group=None, reuse_buffers=False,
-                 graph_exchange=True):
+                 graph_exchange=False):
+        # graph_exchange=True also captures the NCCL all-to-all in the CUDA graph; it hung
+        # on the B200 box with torch 2.11 / NCCL 2.28 (round 1), so it is opt-in.
         import torch.distributed as dist
         self.form, self.basis, self.N, self.group = form, basis, int(N), group
         self.reuse_buffers = bool(reuse_buffers)
@@ -259,9 +262,11 @@ class DistributedAssembler:
             if self._graph is None:
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
+                    if ex.unwritten.numel():
+                        self._out[:ex.nnz][ex.unwritten] = 0.0
                     self.form.assemble_device(self.basis, out=self._out, slot_map=ex.slot_map)
         self._graph.replay()
-        data = self._data if self._graph_has_exchange else ex.finish(self._out)
+        data = self._data if self._graph_has_exchange else ex.finish(self._out, zero=False)
         return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
 
 
