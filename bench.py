@@ -174,7 +174,8 @@ def run_gpu(args):
     if world == 1:
         A = laplace.assemble_device(basis)
     else:
-        da = DistributedAssembler(laplace, basis, l2g, Nglob, ranges, reuse_buffers=True)
+        da = DistributedAssembler(laplace, basis, l2g, Nglob, ranges, reuse_buffers=True,
+                                  graph_exchange=os.environ.get("SKB_GRAPH_EXCHANGE") == "1")
         A = da.assemble()
     torch.cuda.synchronize()
     cold_ms = 1e3 * (time.perf_counter() - t0)

@@ -151,7 +151,7 @@ class InterfaceExchange:
         ``zero=False``: the caller already cleared the receive-only slots."""
         data = out[:self.nnz]
         if zero and self.unwritten.numel():
-            data[self.unwritten] = 0.0
+            data.index_fill_(0, self.unwritten, 0.0)
         if self.world > 1:
             recv = all_to_all_v(out[self.nnz:], self.send_counts_remote, self.recv_counts_remote,
                                 self.group)
@@ -263,7 +263,7 @@ class DistributedAssembler:
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     if ex.unwritten.numel():
-                        self._out[:ex.nnz][ex.unwritten] = 0.0
+                        self._out[:ex.nnz].index_fill_(0, ex.unwritten, 0.0)
                     self.form.assemble_device(self.basis, out=self._out, slot_map=ex.slot_map)
         self._graph.replay()
         data = self._data if self._graph_has_exchange else ex.finish(self._out, zero=False)
