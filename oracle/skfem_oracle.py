@@ -198,6 +198,22 @@ def _lb_tri_p1(X, i):  # element_tri/element_tri_p1.py:18-33
     return y, np.array([0. * x, 1. + 0. * x])
 
 
+def _lb_tri_p2(X, i):  # element_tri/element_tri_p2.py:22-50
+    x, y = X
+    if i == 0:
+        return (1. - 3. * x - 3. * y + 2. * x ** 2 + 4. * x * y + 2. * y ** 2,
+                np.array([-3 + 4. * x + 4. * y, -3 + 4. * x + 4. * y]))
+    if i == 1:
+        return 2. * x ** 2 - x, np.array([4. * x - 1, 0. * x])
+    if i == 2:
+        return 2. * y ** 2 - y, np.array([0. * x, 4. * y - 1])
+    if i == 3:
+        return 4. * x - 4. * x ** 2 - 4. * x * y, np.array([4 - 8. * x - 4. * y, -4. * x])
+    if i == 4:
+        return 4. * x * y, np.array([4. * y, 4. * x])
+    return 4. * y - 4. * x * y - 4. * y ** 2, np.array([-4. * y, 4 - 4. * x - 8. * y])
+
+
 def _lb_tet_p1(X, i):  # element_tet/element_tet_p1.py:19-45
     x, y, z = X
     one, zero = 1 + 0 * x, 0 * x
@@ -259,6 +275,8 @@ ELEMENTS = {
     # name: refdom, nodal, edge, facet, interior dofs, maxdeg, nbf, lbasis
     "tri_p1": dict(refdom="tri", nodal=1, edge=0, facet=0, interior=0,
                    maxdeg=1, nbf=3, lbasis=_lb_tri_p1),
+    "tri_p2": dict(refdom="tri", nodal=1, edge=0, facet=1, interior=0,
+                   maxdeg=2, nbf=6, lbasis=_lb_tri_p2),
     "tet_p1": dict(refdom="tet", nodal=1, edge=0, facet=0, interior=0,
                    maxdeg=1, nbf=4, lbasis=_lb_tet_p1),
     "tet_p2": dict(refdom="tet", nodal=1, edge=1, facet=0, interior=0,
@@ -476,13 +494,35 @@ def cell_basis(m, elem, intorder=None, elements=None, quadrature_rule=None):
 
 def interpolate(basis, w):
     """AbstractBasis.interpolate (abstract_basis.py:271-322), scalar H1."""
-    val = 0
-    grd = 0
-    for i in range(basis.Nbfun):
-        coef = w[basis.element_dofs[i]][:, None]
-        val = val + coef * np.array(basis.basis[i])
-        grd = grd + coef[None] * basis.basis[i].grad
-    return Field(val, grd)
+    if w.shape[0] != basis.N:
+        raise ValueError("Input array has wrong size.")
+
+    def linear_combination(get):
+        out = 0. * np.einsum('...,...j->...j', w[basis.element_dofs[0]], get(basis.basis[0]))
+        for i in range(basis.Nbfun):
+            out += np.einsum('...,...j->...j', w[basis.element_dofs[i]], get(basis.basis[i]))
+        return out
+    return Field(linear_combination(lambda f: np.array(f)),
+                 linear_combination(lambda f: f.grad))
+
+
+def normalize_kwargs(kw, basis):
+    """Form._normalize_asm_kwargs (assembly/form/form.py:91-121)."""
+    out = {}
+    for k, v in kw.items():
+        if isinstance(v, np.ndarray) and v.ndim == 1:
+            out[k] = interpolate(basis, v)
+        elif isinstance(v, np.ndarray) and not isinstance(v, Field):
+            out[k] = Field(v)
+        else:
+            out[k] = v
+    return out
+
+
+def functional_elemental(form, basis, **kw):
+    """Functional.elemental / _kernel (assembly/form/functional.py:19-36)."""
+    w = _W(x=basis.x, h=basis.h, **normalize_kwargs(kw, basis))
+    return (form(w) * basis.dx).sum(-1)
 
 
 # --------------------------------------------------------------------------
@@ -555,37 +595,43 @@ class _W(dict):
         return self[k]
 
 
-def bilinear_coo(form, basis, nthreads=0, **kw):
+def bilinear_coo(form, basis, nthreads=0, vbasis=None, **kw):
     """BilinearForm._assemble (assembly/form/bilinear_form.py:58-128);
     ``nthreads > 0`` restates the reference's Python-thread split of the
-    Nbfun^2 loop (:100-119,153-161)."""
-    nt, nb = basis.nelems, basis.Nbfun
-    w = _W(x=basis.x, h=basis.h, **kw)
-    data = np.zeros((nb, nb, nt))
-    rows = np.zeros(nb * nb * nt, dtype=np.int32)
-    cols = np.zeros(nb * nb * nt, dtype=np.int32)
+    Nbfun^2 loop (:100-119,153-161).  ``basis`` is the trial (u) basis,
+    ``vbasis`` the optional test basis."""
+    ub = basis
+    vb = basis if vbasis is None else vbasis
+    if ub.X.shape[-1] != vb.X.shape[-1]:
+        raise ValueError("Quadrature mismatch: trial and test functions "
+                         "should have same number of integration points.")
+    nt, nb, nbv = ub.nelems, ub.Nbfun, vb.Nbfun
+    w = _W(x=ub.x, h=ub.h, **normalize_kwargs(kw, ub))
+    data = np.zeros((nb, nbv, nt))
+    rows = np.zeros(nb * nbv * nt, dtype=np.int32)
+    cols = np.zeros(nb * nbv * nt, dtype=np.int32)
 
     def kernel(j, i):
-        data[j, i, :] = np.sum(form(basis.basis[j], basis.basis[i], w)
-                               * basis.dx, axis=1)         # :150-151
+        data[j, i, :] = np.sum(form(ub.basis[j], vb.basis[i], w)
+                               * ub.dx, axis=1)            # :150-151
 
     for j in range(nb):
-        for i in range(nb):
-            ixs = slice(nt * (nb * j + i), nt * (nb * j + i + 1))
-            rows[ixs] = basis.element_dofs[i]
-            cols[ixs] = basis.element_dofs[j]
+        for i in range(nbv):
+            ixs = slice(nt * (nbv * j + i), nt * (nbv * j + i + 1))
+            rows[ixs] = vb.element_dofs[i]
+            cols[ixs] = ub.element_dofs[j]
             if nthreads <= 0:
                 kernel(j, i)
     if nthreads > 0:
         from threading import Thread
-        pairs = np.array([[i, j] for j in range(nb) for i in range(nb)])
+        pairs = np.array([[i, j] for j in range(nb) for i in range(nbv)])
         threads = [Thread(target=lambda ix: [kernel(j, i) for i, j in ix], args=(ix,))
                    for ix in np.array_split(pairs, nthreads, axis=0)]
         for th in threads:
             th.start()
         for th in threads:
             th.join()
-    return np.array([rows, cols]), data.flatten('C'), (basis.N, basis.N)
+    return np.array([rows, cols]), data.flatten('C'), (vb.N, ub.N)
 
 
 def coo_to_csr(indices, data, shape):
@@ -602,7 +648,7 @@ def assemble_bilinear(form, basis, **kw):
 def linear_coo(form, basis, **kw):
     """LinearForm._assemble (assembly/form/linear_form.py:18-49)."""
     nt, nb = basis.nelems, basis.Nbfun
-    w = _W(x=basis.x, h=basis.h, **kw)
+    w = _W(x=basis.x, h=basis.h, **normalize_kwargs(kw, basis))
     data = np.zeros(nb * nt)
     rows = np.zeros(nb * nt, dtype=np.int32)
     for i in range(nb):

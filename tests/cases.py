@@ -14,6 +14,8 @@ CASES = {
                            ["unit_load", "user_load"], True),
     "tri_p1_two_triangles": ("tri", "tri_p1", False, ["laplace", "mass"],
                              ["unit_load"], True),
+    "tri_p2_morphed3": ("tri", "tri_p2", False, ["laplace", "mass", "user_aniso"],
+                        ["unit_load", "user_load"], True),
     "tet_p1_tensor6": ("tet", "tet_p1", False,
                        ["laplace", "mass", "user_aniso"],
                        ["unit_load", "user_load"], True),

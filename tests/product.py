@@ -9,7 +9,8 @@ from skfem_b200.models.elasticity import linear_elasticity
 from cases import LAME
 
 MESH = {"tri": fem.MeshTri, "tet": fem.MeshTet, "hex": fem.MeshHex}
-ELEM = {"tri_p1": fem.ElementTriP1, "tet_p1": fem.ElementTetP1, "tet_p2": fem.ElementTetP2,
+ELEM = {"tri_p1": fem.ElementTriP1, "tri_p2": fem.ElementTriP2, "tet_p1": fem.ElementTetP1,
+        "tet_p2": fem.ElementTetP2,
         "hex1": fem.ElementHex1, "hex2": fem.ElementHex2}
 
 

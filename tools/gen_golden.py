@@ -153,6 +153,63 @@ np.savez_compressed(os.path.join(OUT, "hex2_tables.npz"), X=X, W=W,
                     phi=np.array([t[0] for t in tab]),
                     dphi=np.array([t[1] for t in tab]))
 
+# ---- the traced surface: TriP2, coefficient fields (interpolate), Functional,
+# two different bases, asm() with a bare callable, Form.partial -----------------
+mt2 = fem.MeshTri().refined(3)
+mt2 = fem.MeshTri(np.vstack((mt2.p[0] + 0.05 * np.sin(5 * mt2.p[1]), mt2.p[1])), mt2.t)
+dump("tri_p2_morphed3", mt2, fem.ElementTriP2(),
+     bil=[("laplace", laplace), ("mass", mass), ("user_aniso", user_aniso)],
+     lin_=[("unit_load", unit_load), ("user_load", user_load)])
+
+mx = fem.MeshTet.init_tensor(lin(5), lin(4), lin(5))
+mx = fem.MeshTet(morph_pts(mx.p), mx.t)
+b1 = fem.Basis(mx, fem.ElementTetP1())
+b2 = fem.Basis(mx, fem.ElementTetP2(), intorder=2)        # same rule as b1 (4 points)
+prev = np.cos(2. * b1.doflocs[0]) + b1.doflocs[1] * b1.doflocs[2]
+
+
+@fem.BilinearForm
+def newton_like(u, v, w):
+    # coefficient field + its gradient, as in docs/examples/ex10.py
+    return (1. + w['prev'] ** 2) * dot(grad(u), grad(v)) + dot(w['prev'].grad, grad(v)) * u
+
+
+@fem.LinearForm
+def residual_like(v, w):
+    return dot(w['prev'].grad, grad(v)) + w['prev'] * v * w['scale']
+
+
+@fem.Functional
+def energy(w):
+    return 0.5 * dot(w['prev'].grad, w['prev'].grad) + w.x[0] * w['prev']
+
+
+@fem.BilinearForm
+def mixed(u, v, w):
+    return u * v + dot(grad(u), grad(v))
+
+
+def scaled_mass(u, v, w):
+    return w['alpha'] * u * v
+
+
+A_n = newton_like.assemble(b1, prev=prev)
+r_n = residual_like.assemble(b1, prev=prev, scale=2.5)
+A_mix = mixed.assemble(b2, b1)                        # u in P2, v in P1  -> (N1, N2)
+A_asm = fem.asm(scaled_mass, b1, alpha=3.0)
+np.savez_compressed(
+    os.path.join(OUT, "traced_surface.npz"), p=mx.p, t=mx.t, prev=prev,
+    newton_local=newton_like.elemental(b1, prev=prev).data,
+    newton_indptr=A_n.indptr, newton_indices=A_n.indices, newton_data=A_n.data,
+    residual_vec=r_n, energy=np.float64(energy.assemble(b1, prev=prev)),
+    energy_elemental=energy.elemental(b1, prev=prev),
+    mixed_indptr=A_mix.indptr, mixed_indices=A_mix.indices, mixed_data=A_mix.data,
+    mixed_local=mixed.elemental(b2, b1).data, mixed_shape=np.array(A_mix.shape),
+    asm_indptr=A_asm.indptr, asm_indices=A_asm.indices, asm_data=A_asm.data,
+    interp_value=np.asarray(b1.interpolate(prev)), interp_grad=b1.interpolate(prev).grad,
+    doflocs=b1.doflocs)
+print("traced_surface: newton nnz", A_n.nnz, "mixed", A_mix.shape, A_mix.nnz)
+
 # closed-form / known-answer facts
 b = fem.Basis(fem.MeshTri().refined(4), fem.ElementTriP1())
 A = laplace.assemble(b)
