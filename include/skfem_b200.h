@@ -150,8 +150,10 @@ int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *se
  * the rule must be equal), nqp = number of quadrature points.  skb_p1_combine
  * adds, in tile order, the per-tile partial sums of CSR slots touched by more
  * than one tile.  No float atomics: bit-reproducible.                        */
-/* profiling aid for skb_p1tet_laplace_fused: bit0 skips the local-matrix phase,
- * bit1 the slot-reduction phase (results are then meaningless). Default 0.  */
+/* profiling / test switches, default 0.  For skb_p1tet_laplace_fused: bit0 skips
+ * the local-matrix phase, bit1 the slot-reduction phase (results meaningless),
+ * bit2 prints per-role cycle counts of block 0.  bit3: skb_local_bilinear uses
+ * the dense, uncached reference kernel instead of the cached/sparse one.    */
 void skb_debug_flags(int flags);
 int64_t skb_p1_fused_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap, int32_t vcap);
 int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void *rec,

@@ -25,6 +25,10 @@ namespace skb {
 // kernel-launch accounting (skb_launch_count): every launcher reports how many
 // kernels of this library it enqueued
 void count_launch(int n = 1);
+// profiling / test switches set by skb_debug_flags(): bit0 fused kernel skips P1,
+// bit1 skips P2, bit2 prints per-role cycle counts, bit3 forces the dense
+// (uncached) element-local kernel
+int debug_flags();
 
 // ---------------------------------------------------------------------------
 // Correctly rounded a/b for many numerators sharing one denominator.
@@ -180,16 +184,14 @@ __device__ double pw_sum(int n, F &f) {
   if (n <= 128) return pw_leaf(0, n, f);
   int sbase[24], sn[24];
   double sval[24];
-  signed char sstate[24];  // 0: fresh, 1: left done
+  signed char sstate[24];  // 0: fresh, 1: left half pending, 2: right half pending
   int sp = 0;
   sbase[0] = 0; sn[0] = n; sstate[0] = 0;
   double ret = 0.0;
-  bool have_ret = false;
   while (sp >= 0) {
     int cn = sn[sp], cb = sbase[sp];
     if (cn <= 128) {
       ret = pw_leaf(cb, cn, f);
-      have_ret = true;
       --sp;
       continue;
     }
@@ -198,7 +200,6 @@ __device__ double pw_sum(int n, F &f) {
     if (sstate[sp] == 0) {
       sstate[sp] = 1;
       ++sp; sbase[sp] = cb; sn[sp] = n2; sstate[sp] = 0;
-      have_ret = false;
     } else if (sstate[sp] == 1) {
       sval[sp] = ret;  // left result
       sstate[sp] = 2;
@@ -208,7 +209,6 @@ __device__ double pw_sum(int n, F &f) {
       --sp;
     }
   }
-  (void)have_ret;
   return ret;
 }
 

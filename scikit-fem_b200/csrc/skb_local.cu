@@ -191,6 +191,116 @@ local_affine_kernel(const skb_space_t s, int form, double lambda, double two_mu,
 }
 
 // ---------------------------------------------------------------------------
+// Faster variant for rules with nqp <= LOCAL_MAXQ: the pushed gradients of the
+// trial function (per jb) and of the test function (per ib) are computed once
+// per quadrature point and kept in per-thread local memory, and vector-valued
+// integrands are evaluated on their *structurally non-zero* terms only.
+//
+// Skipping a structural zero is exact: in the reference those terms are
+// (0 * x) products added to the running sum, i.e. +-0.0, which leaves every
+// partial sum unchanged (up to the sign of zero; inf/nan gradients excepted -
+// they occur only on zero-volume elements and still give non-finite results).
+// The surviving terms are added in the reference's row-major (i, j) order.
+// ---------------------------------------------------------------------------
+constexpr int LOCAL_MAXQ = 16;
+
+// ddot(C(sym_grad(u)), sym_grad(v)) for u = phi_j e_nu, v = phi_i e_nv, given the
+// scalar gradients gu, gv (models/elasticity.py:35-53, helpers.py:71-73,113-150).
+//   sym_grad(u)[nu][nu] = gu[nu],  [nu][k] = [k][nu] = 0.5*gu[k],  trace = gu[nu]
+//   C(T)[a][b] = 2.*Mu*T[a][b] + Lambda*(a==b ? tr : 0.*tr)
+template <int DIM>
+__device__ __forceinline__ double elasticity_sparse(int nu, int nv, const double *gu,
+                                                    const double *gv, double lambda,
+                                                    double two_mu) {
+  double acc = 0.0;
+  if (nu == nv) {
+    const int n = nu;
+    const double D = (two_mu * gu[n] + lambda * gu[n]) * gv[n];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int b = 0; b < DIM; ++b) {
+        if (a == n && b == n) acc = acc + D;
+        else if (a == n) acc = acc + (two_mu * (0.5 * gu[b])) * (0.5 * gv[b]);
+        else if (b == n) acc = acc + (two_mu * (0.5 * gu[a])) * (0.5 * gv[a]);
+      }
+  } else {
+    const double L = (lambda * gu[nu]) * gv[nv];                    // at (nv, nv)
+    const double M = (two_mu * (0.5 * gu[nv])) * (0.5 * gv[nu]);    // at (nu, nv) and (nv, nu)
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int b = 0; b < DIM; ++b) {
+        if (a == nv && b == nv) acc = acc + L;
+        else if ((a == nu && b == nv) || (a == nv && b == nu)) acc = acc + M;
+      }
+  }
+  return acc;
+}
+
+template <int DIM, bool VEC>
+__global__ void __launch_bounds__(128)
+local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double two_mu,
+                           double *__restrict__ out) {
+  extern __shared__ double smem[];
+  const Tables tab = stage_tables(smem, s);
+  const int nqp = s.nqp, nbs = s.nbs;
+  constexpr int NC = VEC ? DIM : 1;
+  const int nb = nbs * NC;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < s.nel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t eg = s.tind ? (int64_t)s.tind[e] : e;
+    Affine<DIM> g;
+    affine_load<DIM>(g, s.p, s.npts, s.t, s.nel_total, eg);
+    affine_invert(g);
+    const double absdet = fabs(g.det);
+    double gu[LOCAL_MAXQ][DIM], gv[LOCAL_MAXQ][DIM], dxq[LOCAL_MAXQ];
+    for (int q = 0; q < nqp; ++q) dxq[q] = absdet * tab.W[q];       // cell_basis.py:104-105
+    for (int jb = 0; jb < nbs; ++jb) {
+      for (int q = 0; q < nqp; ++q) push_grad<DIM>(g.inv, tab.dphi + jb * DIM * nqp, nqp, q, gu[q]);
+      const double *pj = tab.phi + jb * nqp;
+      for (int ib = 0; ib < nbs; ++ib) {
+        for (int q = 0; q < nqp; ++q)
+          push_grad<DIM>(g.inv, tab.dphi + ib * DIM * nqp, nqp, q, gv[q]);
+        const double *pi = tab.phi + ib * nqp;
+        // nu, nv become compile-time constants after unrolling, which lets the
+        // compiler keep only the structurally non-zero terms of the integrand
+#pragma unroll
+        for (int nu = 0; nu < NC; ++nu)
+#pragma unroll
+          for (int nv = 0; nv < NC; ++nv) {
+            auto f = [&](int q) -> double {
+              double val;
+              if (!VEC) {
+                if (form == SKB_FORM_LAPLACE) {
+                  val = gu[q][0] * gv[q][0];
+#pragma unroll
+                  for (int k = 1; k < DIM; ++k) val = val + gu[q][k] * gv[q][k];
+                } else {
+                  val = pj[q] * pi[q];
+                }
+              } else if (form == SKB_FORM_ELASTICITY) {
+                val = elasticity_sparse<DIM>(nu, nv, gu[q], gv[q], lambda, two_mu);
+              } else if (nu != nv) {
+                val = 0.0;                      // vector Laplace / mass: disjoint components
+              } else if (form == SKB_FORM_VECTOR_LAPLACE) {
+                val = 0.0;                      // row nu of grad(u) against row nu of grad(v)
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) val = val + gu[q][k] * gv[q][k];
+              } else {
+                val = pj[q] * pi[q];            // dot(u, v)
+              }
+              return val * dxq[q];              // bilinear_form.py:151
+            };
+            const int J = jb * NC + nu, I = ib * NC + nv;
+            out[((int64_t)J * nb + I) * s.nel + e] = pw_sum(nqp, f);
+          }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Hexahedra: isoparametric trilinear map (mapping_isoparametric.py:112-226).
 // One CTA per element.  Phase 1: threads over q compute J, det, inv(e,q),
 // dx(e,q) into shared memory.  Phase 2: threads over local entries (j,i),
@@ -312,6 +422,27 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
     k<<<grid, block, smem, st>>>(s, form, lambda, two_mu, out);                              \
     count_launch();                                                                          \
   } while (0)
+#define SKB_LAUNCH_CACHED(D, V)                                                              \
+  do {                                                                                       \
+    auto k = local_affine_cached_kernel<D, V>;                                               \
+    if (smem > 48 * 1024)                                                                    \
+      SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        (int)smem));                                         \
+    k<<<grid, block, smem, st>>>(s, form, lambda, two_mu, out);                              \
+    count_launch();                                                                          \
+  } while (0)
+    // scalar elements: recomputing the push-forward per pair is cheaper than
+    // the local-memory round trip (measured), so only vector elements - whose
+    // dense integrand is 7x more FP64 work - take the cached/sparse kernel
+    if (BILINEAR && vec && s.nqp <= LOCAL_MAXQ && !(debug_flags() & 8)) {
+      if (s.dim == 2 && !vec) SKB_LAUNCH_CACHED(2, false);
+      else if (s.dim == 2 && vec) SKB_LAUNCH_CACHED(2, true);
+      else if (s.dim == 3 && !vec) SKB_LAUNCH_CACHED(3, false);
+      else if (s.dim == 3 && vec) SKB_LAUNCH_CACHED(3, true);
+      else return SKB_EINVAL;
+      return (int)cudaGetLastError();
+    }
+#undef SKB_LAUNCH_CACHED
     if (s.dim == 2 && !vec) SKB_LAUNCH_AFFINE(2, false);
     else if (s.dim == 2 && vec) SKB_LAUNCH_AFFINE(2, true);
     else if (s.dim == 3 && !vec) SKB_LAUNCH_AFFINE(3, false);

@@ -359,8 +359,6 @@ p1_combine_kernel(const double *__restrict__ scratch, const uint32_t *__restrict
   }
 }
 
-static int g_debug = 0;
-
 template <int TT, int NRED, int NR>
 static int launch_fused(const P1Args &a, size_t smem, int sms, bool q4, cudaStream_t st) {
   // persistent grid: as many CTAs per SM as shared memory, threads and
@@ -385,8 +383,6 @@ static int launch_fused(const P1Args &a, size_t smem, int sms, bool q4, cudaStre
 
 }  // namespace skb
 
-extern "C" void skb_debug_flags(int flags) { skb::g_debug = flags; }
-
 extern "C" int64_t skb_p1_fused_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap,
                                            int32_t vcap) {
   return (int64_t)(sizeof(double) * 2 * (10 * (size_t)tile_elems + 2) + 9 * (size_t)vcap * 8 +
@@ -406,7 +402,7 @@ extern "C" int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void
   a.p = p; a.npts = npts; a.rec = (const unsigned char *)rec; a.rec_start = rec_start;
   a.ntiles = ntiles; a.rec_cap = rec_cap; a.vcap = vcap;
   a.csr_data = csr_data; a.scratch = scratch; a.w = w; a.nqp = nqp; a.tame = tame;
-  a.debug = g_debug;
+  a.debug = debug_flags();
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

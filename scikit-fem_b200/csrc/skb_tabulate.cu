@@ -16,6 +16,8 @@ namespace skb {
 
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<int> g_debug{0};
+int debug_flags() { return g_debug.load(std::memory_order_relaxed); }
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
@@ -183,5 +185,7 @@ extern "C" int64_t skb_launch_count(int reset) {
   if (reset) skb::g_launches.store(0);
   return (int64_t)v;
 }
+
+extern "C" void skb_debug_flags(int flags) { skb::g_debug.store(flags); }
 
 extern "C" const char *skb_version(void) { return "skfem_b200 0.1 (sm_100a, fmad=off)"; }

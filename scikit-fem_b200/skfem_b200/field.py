@@ -20,7 +20,6 @@ libm in the last ulp - documented in DESIGN.md.
 from __future__ import annotations
 
 import numbers
-import string
 
 import numpy as np
 import torch
@@ -374,11 +373,12 @@ def einsum(spec, *operands):
         return DeviceArray(pieces[0])
     shape = torch.broadcast_shapes(*[p.shape for p in pieces])
     res = torch.stack([p.expand(shape) for p in pieces])
+    # named output labels first, broadcast ('...') dimensions last: the layout of
+    # every helper ('ij...->ji...', 'i...,j...->ij...', 'ij...,j...->i...')
+    if out is not None and out_has_ell and out_lead and out_named:
+        raise NotImplementedError("einsum outputs of the form '...ij' are not supported "
+                                  "on device fields")
     res = res.reshape(tuple(size[lab] for lab in out_named) + tuple(shape))
-    if out_has_ell and not out_lead:
-        pass  # named labels first, ellipsis last (the 'ij...->ji...' style)
-    elif out_has_ell and out_lead and out is not None and out.endswith("..."):
-        pass
     return DeviceArray(res)
 
 

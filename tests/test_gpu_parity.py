@@ -33,7 +33,6 @@ def test_against_reference_golden(name):
     fs = forms(vector)
     for f in bil:
         coo = fs[f].elemental(b)
-        traced_transcendental = False
         if has_local:
             assert np.array_equal(coo.data, g[f + "_local"]), (name, f)
             assert np.array_equal(coo.indices.shape, (2, coo.data.shape[0]))
@@ -174,6 +173,34 @@ def test_element_subset_and_edge_cases():
     ph[:] = 0.0
     with pytest.raises(Exception, match="Zero Jacobian determinant"):
         laplace.assemble(fem.Basis(fem.MeshHex(ph, gh["t"]), fem.ElementHex1()))
+
+
+def test_dense_and_cached_local_kernels_agree():
+    """skb_local_bilinear has two affine kernels: the dense one evaluates the
+    integrand on zero-padded tensors exactly like the reference, the cached one
+    keeps pushed gradients per quadrature point and skips structural zeros.
+    Their element-local data must be identical (and equal to the reference's)."""
+    from skfem_b200 import _lib
+    cases = [("tet_vp2_elasticity_morphed2", ["elasticity"]),
+             ("tet_vp1_elasticity4", ["elasticity", "vector_laplace", "mass"]),
+             ("tet_p2_morphed3", ["laplace", "mass"]), ("tri_p2_morphed3", ["laplace", "mass"])]
+    try:
+        for name, fl in cases:
+            refdom, ename, vector, _, _, _ = CASES[name]
+            g = load(name)
+            b = fem.Basis(mesh_from(g, refdom), element_from(ename, vector))
+            fs = forms(vector)
+            for f in fl:
+                if getattr(fs[f], "native", None) is None:
+                    continue
+                _lib.lib().skb_debug_flags(0)
+                cached = fs[f].elemental(b).data
+                _lib.lib().skb_debug_flags(8)
+                dense = fs[f].elemental(b).data
+                assert np.array_equal(cached, dense), (name, f)
+                assert np.array_equal(dense, g[f + "_local"]), (name, f)
+    finally:
+        _lib.lib().skb_debug_flags(0)
 
 
 def test_quadrature_mismatch_errors():
