@@ -181,6 +181,32 @@ int skb_tabulate(const skb_space_t *space, int b, double *grad, double *dx, doub
 int skb_qp_reduce(const double *integrand, const double *dx, int64_t nel, int32_t nqp,
                   int sequential, double *out, void *stream);
 
+/* ---- FacetBasis on affine meshes (assembly/basis/facet_basis.py:76-116) ---
+ * Quadrature on `nf` mesh facets.  facets: (dim, nfacets_total) int32 vertex
+ * indices; find[nf] facet indices; tind[nf] / tind_normals[nf] the elements the
+ * trace / the normal are taken from (f2t[side, find] / f2t[0, find]);
+ * lfacet[nf] the local index of each facet in tind_normals (row of t2f);
+ * Xb (dim-1, nqp), Wb (nqp) the rule on the reference facet.  Outputs, any may
+ * be NULL:  x (dim, nf, nqp) = G(Xb) (mapping_affine.py:234-246);  Y (dim, nf,
+ * nqp) = invF(x, tind) (:195-203);  dx (nf, nqp) = |detB| Wb (:170-181, facet_
+ * basis.py:114-115);  normals (dim, nf, nqp) (:248-281);  detabs (nf, nqp).   */
+int skb_facet_geometry(const skb_space_t *space, const int32_t *facets, int64_t nfacets_total,
+                       const int32_t *find, const int32_t *tind, const int32_t *tind_normals,
+                       const int32_t *lfacet, int64_t nf, const double *Xb, const double *Wb,
+                       int32_t nqp, double *x, double *Y, double *dx, double *normals,
+                       double *detabs, void *stream);
+/* Scalar basis function b at the per-facet local points Y: value (nf, nqp)
+ * and, if grad != NULL, the pushed-forward gradient (dim, nf, nqp)
+ * (ElementH1.gbasis, element/element_h1.py:10-18, with lbasis evaluated from
+ * monomial tables: for function b and component c in {phi, d/dx0, ...}
+ * poly_nterm[b*(1+dim)+c] terms, each poly_coef[(b*(1+dim)+c)*12 + k] times the
+ * monomial whose exponents are the bytes of poly_expo[...]; terms are summed
+ * left to right).                                                            */
+int skb_facet_basis(const skb_space_t *space, const int32_t *tind, int64_t nf, int32_t nqp,
+                    const double *Y, const double *poly_coef, const int32_t *poly_expo,
+                    const int32_t *poly_nterm, int32_t b, double *value, double *grad,
+                    void *stream);
+
 /* number of kernels of this library launched so far by this process (the
  * bench's `gpu_launches`); reset != 0 zeroes the counter after reading.     */
 int64_t skb_launch_count(int reset);

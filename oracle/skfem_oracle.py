@@ -492,6 +492,105 @@ def cell_basis(m, elem, intorder=None, elements=None, quadrature_rule=None):
                            dofs_full=edofs)
 
 
+# --------------------------------------------------------------------------
+# FacetBasis (assembly/basis/facet_basis.py:76-140) on affine meshes
+# --------------------------------------------------------------------------
+def f2t_of(m):
+    """Mesh.f2t = build_inverse(t, t2f) (mesh/mesh.py:1085-1100): first and
+    last element touching each facet, -1 when they coincide."""
+    if not hasattr(m, "_f2t"):
+        _, t2f = facets_of(m)
+        flat = t2f.flatten(order='C')
+        owner = np.tile(np.arange(m.t.shape[1]), t2f.shape[0])
+        f_first, ix_first = np.unique(flat, return_index=True)
+        f_last, ix_rev = np.unique(flat[::-1], return_index=True)
+        out = np.zeros((2, flat.max() + 1), dtype=np.int32)
+        out[0, f_first] = owner[ix_first]
+        out[1, f_last] = owner[flat.shape[0] - ix_rev - 1]
+        out[1, out[0] == out[1]] = -1
+        m._f2t = out
+    return m._f2t
+
+
+_NREF = {2: np.array([[0., -1.], [1., 1.], [-1., 0.]]),
+         3: np.array([[0., 0., -1.], [0., -1., 0.], [-1., 0., 0.], [1., 1., 1.]])}
+_BREFDOM = {"tri": "line", "tet": "tri"}
+
+
+def facet_basis(m, elem, intorder=None, facets=None, side=0, quadrature_rule=None):
+    if m.refdom not in _BREFDOM:
+        raise NotImplementedError("affine meshes only")
+    if m.refdom != elem.refdom:
+        raise ValueError("Incompatible Mesh and Element.")
+    edofs, N = dofs(m, elem)
+    fac, t2f = facets_of(m)
+    f2t = f2t_of(m)
+    if quadrature_rule is not None:
+        X, W = quadrature_rule
+    else:
+        X, W = quadrature(_BREFDOM[m.refdom],
+                          intorder if intorder is not None else 2 * elem.maxdeg)
+    find = (np.nonzero(f2t[1] == -1)[0].astype(np.int32) if facets is None
+            else np.asarray(facets))
+    tind, tind_n = f2t[side, find], f2t[0, find]
+    p, dim, nqp, nf = m.p, m.p.shape[0], W.shape[-1], len(find)
+    # boundary mapping (mapping_affine.py:154-181)
+    B = np.empty((dim, dim - 1, fac.shape[1]))
+    c = np.empty((dim, fac.shape[1]))
+    for i in range(dim):
+        c[i] = p[i, fac[0]]
+        for j in range(dim - 1):
+            B[i, j] = p[i, fac[j + 1]] - p[i, fac[0]]
+    if dim == 2:
+        detB = np.sqrt(B[0, 0] ** 2 + B[1, 0] ** 2)
+    else:
+        detB = np.sqrt((B[1, 0] * B[2, 1] - B[2, 0] * B[1, 1]) ** 2 +
+                       (-B[0, 0] * B[2, 1] + B[2, 0] * B[0, 1]) ** 2 +
+                       (B[0, 0] * B[1, 1] - B[1, 0] * B[0, 1]) ** 2)
+    geo = affine_geometry(m)
+    x = (np.einsum('ijk,jl', B[:, :, find], X).T + c[:, find].T).T      # G, :234-246
+    Y = np.einsum('ijk,jkl->ikl', geo.invA[:, :, tind],
+                  (x.T - geo.b[:, tind].T).T)                           # invF, :195-203
+    # normals (:248-281)
+    inv_n = np.einsum('ijk,l->ijkl', geo.invA[:, :, tind_n], np.ones(nqp))
+    Nf = np.empty((dim, nf))
+    for itr in range(_NREF[dim].shape[0]):
+        ix = np.nonzero(t2f[itr, tind_n] == find)[0]
+        for jtr in range(dim):
+            Nf[jtr, ix] = _NREF[dim][itr, jtr]
+    n = np.einsum('ijkl,ik->jkl', inv_n, Nf)
+    n = np.einsum('ijk,jk->ijk', n, 1. / np.sqrt(np.sum(n ** 2, axis=0)))
+    inv = np.einsum('ijk,l->ijkl', geo.invA[:, :, tind], np.ones(nqp))
+    scalar = []
+    for j in range(elem.nbf):                        # element_h1.py:10-18, 3-D X
+        phi, dphi = elem.lbasis(Y, j)
+        scalar.append(Field(np.broadcast_to(phi, (nf, nqp)),
+                            np.einsum('ijkl,ikl->jkl', inv, dphi)))
+    if elem.vector:
+        basis = []
+        for i in range(elem.nbf * elem.dim):
+            f, k = scalar[i // elem.dim], i % elem.dim
+            val = np.zeros((elem.dim,) + f.shape)
+            val[k] = np.array(f)
+            grd = np.zeros((elem.dim,) + f.grad.shape)
+            grd[k] = f.grad
+            basis.append(Field(val, grd))
+    else:
+        basis = scalar
+    detDG = np.tile(detB[find], (nqp, 1)).T
+    dx = np.abs(detDG) * np.broadcast_to(W, (nf, nqp))                  # facet_basis.py:114
+    h = np.abs(detDG) ** (1. / (dim - 1.))
+    return SimpleNamespace(mesh=m, elem=elem, X=X, W=W, basis=basis, dx=dx,
+                           element_dofs=edofs[:, tind], N=N, Nbfun=len(basis),
+                           nelems=nf, x=Field(x), h=Field(h), extra=dict(n=Field(n)),
+                           find=find, tind=tind, Y=Y, dofs_full=edofs)
+
+
+def _params(basis, kw):
+    return _W(x=basis.x, h=basis.h, **getattr(basis, "extra", {}),
+              **normalize_kwargs(kw, basis))
+
+
 def interpolate(basis, w):
     """AbstractBasis.interpolate (abstract_basis.py:271-322), scalar H1."""
     if w.shape[0] != basis.N:
@@ -521,7 +620,7 @@ def normalize_kwargs(kw, basis):
 
 def functional_elemental(form, basis, **kw):
     """Functional.elemental / _kernel (assembly/form/functional.py:19-36)."""
-    w = _W(x=basis.x, h=basis.h, **normalize_kwargs(kw, basis))
+    w = _params(basis, kw)
     return (form(w) * basis.dx).sum(-1)
 
 
@@ -606,7 +705,7 @@ def bilinear_coo(form, basis, nthreads=0, vbasis=None, **kw):
         raise ValueError("Quadrature mismatch: trial and test functions "
                          "should have same number of integration points.")
     nt, nb, nbv = ub.nelems, ub.Nbfun, vb.Nbfun
-    w = _W(x=ub.x, h=ub.h, **normalize_kwargs(kw, ub))
+    w = _params(ub, kw)
     data = np.zeros((nb, nbv, nt))
     rows = np.zeros(nb * nbv * nt, dtype=np.int32)
     cols = np.zeros(nb * nbv * nt, dtype=np.int32)
@@ -648,7 +747,7 @@ def assemble_bilinear(form, basis, **kw):
 def linear_coo(form, basis, **kw):
     """LinearForm._assemble (assembly/form/linear_form.py:18-49)."""
     nt, nb = basis.nelems, basis.Nbfun
-    w = _W(x=basis.x, h=basis.h, **normalize_kwargs(kw, basis))
+    w = _params(basis, kw)
     data = np.zeros(nb * nt)
     rows = np.zeros(nb * nt, dtype=np.int32)
     for i in range(nb):

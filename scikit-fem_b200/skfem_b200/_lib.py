@@ -52,6 +52,9 @@ SIGNATURES = {
     "skb_p1_fused_smem_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "skb_debug_flags": (None, [_INT]),
     "skb_p1_combine": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
+    "skb_facet_geometry": (_INT, [_SP, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I32,
+                                  _P, _P, _P, _P, _P, _P]),
+    "skb_facet_basis": (_INT, [_SP, _P, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P, _P]),
     "skb_launch_count": (_I64, [_INT]),
     "skb_version": (C.c_char_p, []),
 }

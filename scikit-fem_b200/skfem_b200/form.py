@@ -352,6 +352,8 @@ class BilinearForm(Form):
     def _native_applicable(self, ubasis, vbasis, kwargs):
         if self.native is None or kwargs or (vbasis is not None and vbasis is not ubasis):
             return False
+        if not getattr(ubasis, "_native_ok", True):   # FacetBasis: traced path
+            return False
         kind, _, _, field = self.native
         if kind != "bilinear":
             return False
@@ -481,7 +483,7 @@ class LinearForm(Form):
         d = basis._dev()
         out = torch.empty((basis.Nbfun, basis.nelems), dtype=torch.float64, device=d["device"])
         if (self.native is not None and not kwargs and self.native[0] == "linear"
-                and basis.ncomp == 1):
+                and basis.ncomp == 1 and getattr(basis, "_native_ok", True)):
             code = _lib.lib().skb_local_linear(C.byref(d["space"]), self.native[1], None,
                                                out.data_ptr(), _stream())
             _lib.check(code, "skb_local_linear")

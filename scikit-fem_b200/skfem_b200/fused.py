@@ -67,6 +67,8 @@ def applicable(basis, form):
     from .element import ElementTetP1
     if form.native is None or form.native[1] != _lib.FORM_LAPLACE:
         return False
+    if not getattr(basis, "_native_ok", True):
+        return False
     if not isinstance(basis.elem, ElementTetP1) or not basis._affine:
         return False
     W = basis.W

@@ -176,6 +176,35 @@ class Mesh:
         ckey = np.unique(cand[0].astype(np.int64) * nv + cand[1])
         return np.nonzero(np.isin(key, ckey))[0].astype(np.int32)
 
+    boundaries = None  # optional {name: facet indices}
+
+    def facets_satisfying(self, test, boundaries_only=False):
+        """Facets whose midpoints satisfy ``test`` (mesh.py:426-446)."""
+        midp = self.p[:, self.facets].mean(axis=1)
+        facets = np.nonzero(test(midp))[0].astype(np.int32)
+        if boundaries_only:
+            facets = np.intersect1d(facets, self.boundary_facets())
+        return facets
+
+    def normalize_facets(self, facets):
+        """Array of facet indices from an index, an array, a list of criteria,
+        a callable on facet midpoints or a boundary name (mesh.py:1291-1329)."""
+        if isinstance(facets, (int, np.integer)):
+            return np.array([facets])
+        if isinstance(facets, np.ndarray):
+            return facets
+        if facets is None:
+            return self.boundary_facets()
+        if isinstance(facets, (tuple, list, set)):
+            return np.unique(np.concatenate([self.normalize_facets(f) for f in facets]))
+        if callable(facets):
+            return self.facets_satisfying(facets)
+        if isinstance(facets, str):
+            if self.boundaries is not None and facets in self.boundaries:
+                return self.boundaries[facets]
+            raise ValueError("Boundary '{}' not found.".format(facets))
+        raise NotImplementedError
+
     def normalize_elements(self, elements):
         if isinstance(elements, (int, np.integer)):
             return np.array([elements], dtype=np.int32)

@@ -82,6 +82,27 @@ def test_boundary_dofs():
     assert np.array_equal(np.sort(D), on_bnd)
 
 
+@pytest.mark.parametrize("name,M,E", [
+    ("facet_tri_p1", "MeshTri", "ElementTriP1"), ("facet_tri_p2", "MeshTri", "ElementTriP2"),
+    ("facet_tet_p1", "MeshTet", "ElementTetP1"), ("facet_tet_p2", "MeshTet", "ElementTetP2")])
+def test_facet_basis_host_side_matches_reference(name, M, E):
+    """facets / f2t / find / tind / facet rule / element_dofs of FacetBasis
+    (no device work in the constructor)."""
+    g = load(name)
+    m = getattr(fem, M)(g["p"], g["t"])
+    fb = fem.FacetBasis(m, getattr(fem, E)())
+    assert np.array_equal(m.facets, g["facets"]) and np.array_equal(m.f2t, g["f2t"])
+    assert np.array_equal(fb.find, g["find"]) and np.array_equal(fb.tind, g["tind"])
+    assert np.array_equal(fb.X, g["X"]) and np.array_equal(fb.W, g["W"])
+    assert np.array_equal(fb.element_dofs, g["element_dofs"]) and fb.N == int(g["N"])
+    sub = m.facets_satisfying(lambda x: x[0] < 0.3, boundaries_only=True)
+    assert np.array_equal(sub, g["sub_find"])
+    assert np.array_equal(m.normalize_facets([sub[:3], int(sub[-1])]),
+                          np.unique(np.r_[sub[:3], sub[-1]]))
+    with pytest.raises(ValueError, match="not found"):
+        m.normalize_facets("left")
+
+
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "skfem_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
