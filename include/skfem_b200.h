@@ -207,6 +207,30 @@ int skb_facet_basis(const skb_space_t *space, const int32_t *tind, int64_t nf, i
                     const int32_t *poly_nterm, int32_t b, double *value, double *grad,
                     void *stream);
 
+/* ---- boundary conditions on the device CSR ------------
+ * skfem.utils.enforce (utils.py:327-400): for every r in D[nD] the stored
+ * entries of row r become 0.0 (they stay in the pattern) and the diagonal
+ * entry becomes diag; *missing_diag (device int32, caller-zeroed) is set to 1
+ * if a row of D has no stored diagonal (the reference would insert one).    */
+int skb_csr_enforce(const int32_t *indptr, const int32_t *indices, double *data,
+                    const int32_t *D, int64_t nD, double diag, int32_t *missing_diag,
+                    void *stream);
+/* skfem.utils.condense (utils.py:462-603) for ascending index sets: rows I[nI],
+ * columns with colmap[col] >= 0 (colmap: int32[ncols], new column index or -1).
+ * Pass 1 writes the per-row entry counts; the caller scans them into
+ * new_indptr[nI+1]; pass 2 writes new_indices / new_data (= A[I][:, I]) and, if
+ * bout != NULL, bout[k] = b[I[k]] - sum over dropped columns c of a*x[c], added
+ * left to right from 0.0 (scipy csr_matvec order: bit-identical).            */
+int skb_csr_condense_count(const int32_t *indptr, const int32_t *indices, const int32_t *I,
+                           int64_t nI, const int32_t *colmap, int32_t *counts, void *stream);
+int skb_csr_condense_fill(const int32_t *indptr, const int32_t *indices, const double *data,
+                          const int32_t *I, int64_t nI, const int32_t *colmap,
+                          const int32_t *new_indptr, int32_t *new_indices, double *new_data,
+                          const double *x, const double *b, double *bout, void *stream);
+/* y = A x with the row sums in scipy's csr_matvec order (hand-off to solvers) */
+int skb_csr_spmv(const int32_t *indptr, const int32_t *indices, const double *data,
+                 const double *x, double *y, int64_t nrows, void *stream);
+
 /* number of kernels of this library launched so far by this process (the
  * bench's `gpu_launches`); reset != 0 zeroes the counter after reading.     */
 int64_t skb_launch_count(int reset);

@@ -803,3 +803,62 @@ def pairwise_sum(a):
     n2 = n // 2
     n2 -= n2 % 8
     return pairwise_sum(a[:n2]) + pairwise_sum(a[n2:])
+
+
+# --------------------------------------------------------------------------
+# boundary conditions (utils.py:282-400, 462-603), restated entry by entry
+# --------------------------------------------------------------------------
+def enforce(A, b=None, x=None, D=None, diag=1.):
+    """skfem.utils.enforce: rows D zeroed in place in the pattern, diagonal set."""
+    A = A.tocsr().copy()
+    if x is None:
+        x = np.zeros(A.shape[0])
+    for r in np.asarray(D):
+        found = False
+        for s in range(A.indptr[r], A.indptr[r + 1]):
+            on_diag = A.indices[s] == r
+            A.data[s] = diag if on_diag else 0.
+            found |= bool(on_diag)
+        assert found, "missing diagonal"
+    if b is None:
+        return A
+    if hasattr(b, "tocsr"):
+        return A, enforce(b, D=D, diag=0.)
+    bout = b.copy()
+    bout[D] = x[D]
+    return A, bout
+
+
+def condense(A, b=None, x=None, D=None):
+    """skfem.utils.condense for D given: (A[I][:, I], b[I] - A[I][:, D] @ x[D], I),
+    the matrix-vector product accumulated like scipy's csr_matvec."""
+    from scipy.sparse import csr_matrix
+    A = A.tocsr()
+    n = A.shape[0]
+    I = np.setdiff1d(np.arange(n, dtype=np.int32), D)
+    if x is None:
+        x = np.zeros(n)
+    elif b is None:
+        b = np.zeros_like(x)
+    colmap = np.full(n, -1, dtype=np.int64)
+    colmap[I] = np.arange(len(I))
+    indptr, indices, data, bout = [0], [], [], []
+    for r in I:
+        y = 0.
+        for s in range(A.indptr[r], A.indptr[r + 1]):
+            c = A.indices[s]
+            if colmap[c] >= 0:
+                indices.append(colmap[c])
+                data.append(A.data[s])
+            else:
+                y = y + A.data[s] * x[c]
+        indptr.append(len(indices))
+        if b is not None and not hasattr(b, "tocsr"):
+            bout.append(b[r] - y)
+    AII = csr_matrix((np.array(data), np.array(indices, dtype=np.int32),
+                      np.array(indptr, dtype=np.int32)), shape=(len(I), len(I)))
+    if b is None:
+        return AII, None, I
+    if hasattr(b, "tocsr"):
+        return AII, condense(b, D=D)[0], I
+    return AII, np.array(bout), I

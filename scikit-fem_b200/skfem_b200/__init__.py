@@ -21,7 +21,8 @@ from .facet_basis import FacetBasis, BoundaryFacetBasis
 from .field import DiscreteField, DeviceArray, asdevice
 from .form import (Form, BilinearForm, LinearForm, Functional, COOData, DeviceCSR,
                    FormExtraParams, asm)
-from . import helpers, models, quadrature
+from .utils import enforce, condense, solve, solver_iter_pcg
+from . import helpers, models, quadrature, utils
 
 InteriorBasis = CellBasis  # deprecated alias kept by the reference
 
@@ -35,4 +36,5 @@ __all__ = [
     "FacetBasis", "BoundaryFacetBasis",
     "DiscreteField", "DeviceArray", "asdevice", "Form", "BilinearForm", "LinearForm",
     "Functional", "COOData", "DeviceCSR", "FormExtraParams", "asm", "helpers", "models",
+    "enforce", "condense", "solve", "solver_iter_pcg", "utils",
 ]

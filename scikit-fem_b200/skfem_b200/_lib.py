@@ -55,6 +55,10 @@ SIGNATURES = {
     "skb_facet_geometry": (_INT, [_SP, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I32,
                                   _P, _P, _P, _P, _P, _P]),
     "skb_facet_basis": (_INT, [_SP, _P, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P, _P]),
+    "skb_csr_enforce": (_INT, [_P, _P, _P, _P, _I64, C.c_double, _P, _P]),
+    "skb_csr_condense_count": (_INT, [_P, _P, _P, _I64, _P, _P, _P]),
+    "skb_csr_condense_fill": (_INT, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "skb_csr_spmv": (_INT, [_P, _P, _P, _P, _P, _I64, _P]),
     "skb_launch_count": (_I64, [_INT]),
     "skb_version": (C.c_char_p, []),
 }

@@ -104,6 +104,21 @@ class DeviceCSR:
 
     tocsr = to_scipy
 
+    def copy(self):
+        """New values, shared (immutable) pattern."""
+        return DeviceCSR(self.indptr, self.indices, self.data.clone(), self.shape)
+
+    @classmethod
+    def from_scipy(cls, A, device=None):
+        torch = _torch()
+        from .basis import default_device
+        device = default_device() if device is None else device
+        A = A.tocsr()
+        A.sort_indices()
+        return cls(torch.as_tensor(A.indptr.astype(np.int32), device=device),
+                   torch.as_tensor(A.indices.astype(np.int32), device=device),
+                   torch.as_tensor(A.data.astype(np.float64), device=device), A.shape)
+
     def to_torch(self):
         torch = _torch()
         return torch.sparse_csr_tensor(self.indptr.long(), self.indices.long(), self.data,
