@@ -174,8 +174,11 @@ def run_gpu(args):
     if world == 1:
         A = laplace.assemble_device(basis)
     else:
+        # pipelined: the interface exchange of step i overlaps the local kernels of
+        # step i+1 (two output buffer sets); SKB_PIPELINE=0 serialises them again
         da = DistributedAssembler(laplace, basis, l2g, Nglob, ranges, reuse_buffers=True,
-                                  graph_exchange=os.environ.get("SKB_GRAPH_EXCHANGE") == "1")
+                                  graph_exchange=os.environ.get("SKB_GRAPH_EXCHANGE") == "1",
+                                  pipeline=os.environ.get("SKB_PIPELINE", "1") == "1")
         A = da.assemble()
     torch.cuda.synchronize()
     cold_ms = 1e3 * (time.perf_counter() - t0)
@@ -215,17 +218,24 @@ def run_gpu(args):
         step = step_eager
     for _ in range(max(args.warmup, 3)):
         step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    # the clock sampler (an nvidia-smi subprocess on rank 0) is started BEFORE the
+    # barrier: spawning it takes ~1 ms, which the other ranks would otherwise spend
+    # inside their timed region waiting for rank 0 at the first exchange
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    if world > 1:
+        da.wait()
+        torch.cuda.synchronize()
+        dist.barrier()
+    torch.cuda.synchronize()
     _lib.lib().skb_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step()
+    if da is not None:
+        da.wait()                    # the last exchanges (side stream) are part of the K steps
     ev1.record()
     torch.cuda.synchronize()
     launches = int(_lib.lib().skb_launch_count(0))
@@ -289,7 +299,7 @@ def run_gpu(args):
     nverts = m.p.shape[1]
     fused_stats = None
     for k, v in basis._plans.items():
-        if isinstance(k, tuple) and k and k[0] == "fused":
+        if isinstance(k, tuple) and k and k[0] in ("fused", "fused-mapped") and v is not None:
             from skfem_b200 import fused as _fused
             fused_stats = _fused.stats(v)
             fused_stats["tile"], fused_stats["threads"], fused_stats["ring"] = v.T, v.threads, v.ring
@@ -316,7 +326,9 @@ def run_gpu(args):
                                 if world == 1 else
                                 "MeshTet.init_tensor z-slab of {0}^3 cells per GPU, {1} slabs, "
                                 "ElementTetP1 laplace, warm re-assembly into a row-partitioned "
-                                "CSR, interface rows exchanged over NCCL".format(cells, world)),
+                                "CSR, interface rows exchanged over NCCL{2}".format(
+                                    cells, world, " (exchange of step i overlapped with the "
+                                    "local kernels of step i+1)" if da.pipeline else "")),
                    "elements_per_gpu": nel, "dofs_per_gpu": basis.N, "nnz_per_gpu": nnz,
                    "nnz_total": nnz_total,
                    "interface_bytes_sent_rank0": (da.exchange.bytes_per_exchange

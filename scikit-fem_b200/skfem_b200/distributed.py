@@ -178,9 +178,16 @@ class DistributedCSR:
     """Row block of the global matrix owned by this rank: rows
     ``[row0, row0+nrows)``, global column indices."""
 
-    def __init__(self, indptr, indices, data, row0, shape):
+    def __init__(self, indptr, indices, data, row0, shape, ready=None):
         self.indptr, self.indices, self.data = indptr, indices, data
         self.row0, self.shape = int(row0), tuple(shape)
+        self.ready = ready     # CUDA event after which `data` is complete (pipelined mode)
+
+    def wait(self):
+        """Make the current stream wait until the values are complete."""
+        if self.ready is not None:
+            _torch().cuda.current_stream().wait_event(self.ready)
+        return self
 
     @property
     def nnz(self):
@@ -189,6 +196,7 @@ class DistributedCSR:
     def to_scipy_block(self):
         from scipy.sparse import csr_matrix
         nrows = int(self.indptr.shape[0]) - 1
+        self.wait()
         return csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
                            self.indptr.cpu().numpy()), shape=(nrows, self.shape[1]))
 
@@ -203,13 +211,20 @@ class DistributedAssembler:
     """
 
     def __init__(self, form, basis, l2g, N, ranges=None, group=None, reuse_buffers=False,
-                 graph_exchange=False):
+                 graph_exchange=False, pipeline=False):
         # graph_exchange=True also captures the NCCL all-to-all in the CUDA graph; it hung
         # on the B200 box with torch 2.11 / NCCL 2.28 (round 1), so it is opt-in.
         import torch.distributed as dist
         self.form, self.basis, self.N, self.group = form, basis, int(N), group
         self.reuse_buffers = bool(reuse_buffers)
         self.graph_exchange = bool(graph_exchange)
+        # pipeline=True (with reuse_buffers): two output buffer sets; the interface
+        # exchange + ordered add of step i run on a side stream while the local
+        # kernels of step i+1 run on the caller's stream.  The returned block
+        # carries the event that completes it (DistributedCSR.wait) and is
+        # overwritten two calls later.
+        self.pipeline = bool(pipeline) and self.reuse_buffers
+        self._sets = None
         self._graph = self._out = self._data = None
         self._graph_has_exchange = False
         self.world = dist.get_world_size(group)
@@ -237,6 +252,8 @@ class DistributedAssembler:
             self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
             data = ex.finish(out)
             return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
+        if self.pipeline:
+            return self._assemble_pipelined()
         # re-assembly loop mode: persistent output buffer, the local kernels are
         # replayed from a CUDA graph, only the NCCL exchange is issued eagerly.
         # The returned block aliases the internal buffer (overwritten next call).
@@ -268,6 +285,50 @@ class DistributedAssembler:
         self._graph.replay()
         data = self._data if self._graph_has_exchange else ex.finish(self._out, zero=False)
         return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
+
+
+def _assemble_pipelined(self):
+    torch = _torch()
+    ex = self.exchange
+    cur = torch.cuda.current_stream()
+    if self._sets is None:
+        dev = ex.slot_map.device
+        self._comm = torch.cuda.Stream(device=dev)
+        self._sets, self._flip = [], 0
+        for _ in range(2):
+            out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64, device=dev)
+            self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)  # plan, warm
+            ex.finish(out)                                                         # NCCL warm
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if ex.unwritten.numel():
+                    out[:ex.nnz].index_fill_(0, ex.unwritten, 0.0)
+                self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
+            self._sets.append({"out": out, "graph": g,
+                               "computed": torch.cuda.Event(), "done": torch.cuda.Event()})
+    st = self._sets[self._flip]
+    self._flip ^= 1
+    cur.wait_event(st["done"])            # the exchange that last read this set is over
+    st["graph"].replay()
+    st["computed"].record(cur)
+    with torch.cuda.stream(self._comm):
+        self._comm.wait_event(st["computed"])
+        data = ex.finish(st["out"], zero=False)
+        st["done"].record(self._comm)
+    return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N),
+                          ready=st["done"])
+
+def wait(self):
+    """Current stream waits for every outstanding exchange (pipelined mode)."""
+    if self._sets:
+        cur = _torch().cuda.current_stream()
+        for st in self._sets:
+            cur.wait_event(st["done"])
+
+
+DistributedAssembler._assemble_pipelined = _assemble_pipelined
+DistributedAssembler.wait = wait
 
 
 def slab_mesh_tet(cells_xy, cells_z, rank, world, mesh_cls=None):

@@ -48,6 +48,24 @@ def _worker(rank, world, port, cxy, cz, out):
             assert np.array_equal(A.indices.cpu().numpy(), blk.indices)
             np.testing.assert_allclose(A.data.cpu().numpy(), blk.data, rtol=1e-12,
                                        atol=1e-12 * np.abs(blk.data).max())
+        # re-assembly loop modes: persistent buffers + CUDA graph, and the pipelined
+        # variant (exchange of step i overlapped with the kernels of step i+1)
+        for kw in (dict(reuse_buffers=True), dict(reuse_buffers=True, pipeline=True)):
+            dp = DistributedAssembler(laplace, fem.Basis(m, fem.ElementTetP1()), l2g, N, ranges,
+                                      **kw)
+            dp.assemble()
+            blocks = []
+            for _ in range(5):           # back to back, no host synchronisation in between
+                blocks.append(dp.assemble().wait().data.clone())
+            dp.wait()
+            torch.cuda.synchronize()
+            for d in blocks:
+                assert torch.equal(d, A2.data), kw
+            last = [dp.assemble() for _ in range(6)][-2:]     # fully overlapped
+            dp.wait()
+            torch.cuda.synchronize()
+            for A in last:
+                assert torch.equal(A.data, A2.data), kw
         out[rank] = 1
     finally:
         dist.destroy_process_group()
