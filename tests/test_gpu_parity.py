@@ -301,3 +301,31 @@ def test_baseline_config2_full_size_properties():
     M = mass.assemble(b)
     np.testing.assert_allclose(M.sum(), 1.0, rtol=1e-11)
     np.testing.assert_allclose(M @ np.ones(b.N), f, rtol=1e-10, atol=1e-18)
+
+
+def test_device_topology_matches_reference_numbering():
+    """Meshes above 65 536 elements build edges / facets with the packed-key sort
+    on the GPU (mesh._build_entities_device); results must equal the oracle's
+    np.unique(axis=1) restatement of Mesh.build_entities (mesh.py:1065-1082),
+    and with them the P2 DOF numbering."""
+    from oracle import skfem_oracle as O
+    from skfem_b200.mesh import _build_entities_device
+    x = np.linspace(0, 1, 26)                     # 93 750 tets
+    m = fem.MeshTet.init_tensor(x, x, np.linspace(0, 2, 26))
+    om = O.mesh_tet_tensor(x, x, np.linspace(0, 2, 26))
+    assert m.nelements >= (1 << 16)
+    e, t2e = O.edges_of(om)
+    f, t2f = O.facets_of(om)
+    assert np.array_equal(m.edges, e) and np.array_equal(m.t2e, t2e)
+    assert np.array_equal(m.facets, f) and np.array_equal(m.t2f, t2f)
+    assert m.edges.dtype == e.dtype and m.t2e.dtype == t2e.dtype
+    b = fem.Basis(m, fem.ElementTetP2())
+    edofs, N = O.dofs(om, O.element("tet_p2"))
+    assert b.N == N and np.array_equal(b.element_dofs, edofs)
+    # unsorted representatives (hex-style facets: first occurrence), small enough to pack
+    xh = np.linspace(0, 1, 12)
+    mh = fem.MeshHex.init_tensor(xh, xh, xh)
+    oh = O.mesh_hex_tensor(xh, xh, xh)
+    fh, t2fh = O.facets_of(oh)
+    got_f, got_t2f = _build_entities_device(mh.t, mh.refdom.facets, int(mh.t.max()) + 1, False)
+    assert np.array_equal(got_f, fh) and np.array_equal(got_t2f, t2fh)
