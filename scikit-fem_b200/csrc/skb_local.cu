@@ -381,6 +381,8 @@ local_hex_kernel(const skb_space_t s, int form, double *__restrict__ out, int *_
   }
 }
 
+int launch_hex_mma(const skb_space_t &s, int form, double *out, int *err, cudaStream_t st);
+
 static int grid_for(int64_t work_items, int block, int per_sm) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -458,12 +460,21 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
     int *err = nullptr;
     SKB_CUDA_TRY(cudaMallocAsync((void **)&err, sizeof(int), st));
     SKB_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
-    auto k = local_hex_kernel<BILINEAR>;
-    if (smem > 48 * 1024)
-      SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = grid_for(s.nel * 256, 256, 8);
-    k<<<grid, 256, smem, st>>>(s, form, out, err);
-    count_launch();
+    if (BILINEAR && s.nbs > 8 && s.nbs <= 32 && (form == SKB_FORM_LAPLACE || form == SKB_FORM_MASS) &&
+        !(debug_flags() & 8)) {
+      // high-order hexes (value-level parity): Gram-matrix contraction on the FP64
+      // tensor cores, csrc/skb_hex_mma.cu; debug bit 3 keeps the scalar kernel
+      const int rc = launch_hex_mma(s, form, out, err, st);
+      if (rc != SKB_OK) return rc;
+    } else {
+      auto k = local_hex_kernel<BILINEAR>;
+      if (smem > 48 * 1024)
+        SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+      const int grid = grid_for(s.nel * 256, 256, 8);
+      k<<<grid, 256, smem, st>>>(s, form, out, err);
+      count_launch();
+    }
     int herr = 0;
     SKB_CUDA_TRY(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     SKB_CUDA_TRY(cudaStreamSynchronize(st));
