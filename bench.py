@@ -268,7 +268,9 @@ def run_gpu(args):
             # every rank: its slab in, its row block of the global matrix out
             return DistributedAssembler(laplace, bb, l2g, Nglob, ranges).assemble() \
                 .to_scipy_block()
-        for _ in range(2):
+        # warm-up: the first calls also populate torch's pinned-host allocator pool for the
+        # three result arrays (cudaHostAlloc of 90 MB costs tens of ms; tools/profile_e2e.py)
+        for _ in range(max(args.warmup, 4)):
             Ah = e2e_step()
         if world > 1:
             dist.barrier()
