@@ -286,49 +286,44 @@ class DistributedAssembler:
         data = self._data if self._graph_has_exchange else ex.finish(self._out, zero=False)
         return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N))
 
+    def _assemble_pipelined(self):
+        torch = _torch()
+        ex = self.exchange
+        cur = torch.cuda.current_stream()
+        if self._sets is None:
+            dev = ex.slot_map.device
+            self._comm = torch.cuda.Stream(device=dev)
+            self._sets, self._flip = [], 0
+            for _ in range(2):
+                out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64, device=dev)
+                self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)  # plan, warm
+                ex.finish(out)                                                         # NCCL warm
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    if ex.unwritten.numel():
+                        out[:ex.nnz].index_fill_(0, ex.unwritten, 0.0)
+                    self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
+                self._sets.append({"out": out, "graph": g,
+                                   "computed": torch.cuda.Event(), "done": torch.cuda.Event()})
+        st = self._sets[self._flip]
+        self._flip ^= 1
+        cur.wait_event(st["done"])            # the exchange that last read this set is over
+        st["graph"].replay()
+        st["computed"].record(cur)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(st["computed"])
+            data = ex.finish(st["out"], zero=False)
+            st["done"].record(self._comm)
+        return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N),
+                              ready=st["done"])
 
-def _assemble_pipelined(self):
-    torch = _torch()
-    ex = self.exchange
-    cur = torch.cuda.current_stream()
-    if self._sets is None:
-        dev = ex.slot_map.device
-        self._comm = torch.cuda.Stream(device=dev)
-        self._sets, self._flip = [], 0
-        for _ in range(2):
-            out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64, device=dev)
-            self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)  # plan, warm
-            ex.finish(out)                                                         # NCCL warm
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                if ex.unwritten.numel():
-                    out[:ex.nnz].index_fill_(0, ex.unwritten, 0.0)
-                self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
-            self._sets.append({"out": out, "graph": g,
-                               "computed": torch.cuda.Event(), "done": torch.cuda.Event()})
-    st = self._sets[self._flip]
-    self._flip ^= 1
-    cur.wait_event(st["done"])            # the exchange that last read this set is over
-    st["graph"].replay()
-    st["computed"].record(cur)
-    with torch.cuda.stream(self._comm):
-        self._comm.wait_event(st["computed"])
-        data = ex.finish(st["out"], zero=False)
-        st["done"].record(self._comm)
-    return DistributedCSR(ex.indptr, ex.indices, data, ex.row0, (self.N, self.N),
-                          ready=st["done"])
-
-def wait(self):
-    """Current stream waits for every outstanding exchange (pipelined mode)."""
-    if self._sets:
-        cur = _torch().cuda.current_stream()
-        for st in self._sets:
-            cur.wait_event(st["done"])
-
-
-DistributedAssembler._assemble_pipelined = _assemble_pipelined
-DistributedAssembler.wait = wait
+    def wait(self):
+        """Current stream waits for every outstanding exchange (pipelined mode)."""
+        if self._sets:
+            cur = _torch().cuda.current_stream()
+            for st in self._sets:
+                cur.wait_event(st["done"])
 
 
 def slab_mesh_tet(cells_xy, cells_z, rank, world, mesh_cls=None):
