@@ -657,6 +657,53 @@ def eye(w, n):
                      for j in range(n)])
 
 
+def identity(w, N=None):                        # helpers.py:153-161
+    if N is None:
+        N = w.shape[-3]
+    return eye(np.ones(w.shape[-2:]), N)
+
+
+def div(u):                                     # helpers.py:27-36
+    if len(u.grad.shape) == 4:
+        return np.einsum('ii...', u.grad)
+    return u.grad[0]
+
+
+def mul(A, x):                                  # helpers.py:132-134
+    return np.einsum('ij...,j...->i...', A, x)
+
+
+def det(A):                                     # helpers.py:164-176
+    if A.shape[0] == 3:
+        return A[0, 0] * (A[1, 1] * A[2, 2] - A[1, 2] * A[2, 1]) - \
+            A[0, 1] * (A[1, 0] * A[2, 2] - A[1, 2] * A[2, 0]) + \
+            A[0, 2] * (A[1, 0] * A[2, 1] - A[1, 1] * A[2, 0])
+    return A[0, 0] * A[1, 1] - A[1, 0] * A[0, 1]
+
+
+def inv(A):                                     # helpers.py:179-207
+    out = np.zeros_like(A)
+    d = det(A)
+    if A.shape[0] == 3:
+        out[0, 0] = (-A[1, 2] * A[2, 1] + A[1, 1] * A[2, 2]) / d
+        out[1, 0] = (A[1, 2] * A[2, 0] - A[1, 0] * A[2, 2]) / d
+        out[2, 0] = (-A[1, 1] * A[2, 0] + A[1, 0] * A[2, 1]) / d
+        out[0, 1] = (A[0, 2] * A[2, 1] - A[0, 1] * A[2, 2]) / d
+        out[1, 1] = (-A[0, 2] * A[2, 0] + A[0, 0] * A[2, 2]) / d
+        out[2, 1] = (A[0, 1] * A[2, 0] - A[0, 0] * A[2, 1]) / d
+        out[0, 2] = (-A[0, 2] * A[1, 1] + A[0, 1] * A[1, 2]) / d
+        out[1, 2] = (A[0, 2] * A[1, 0] - A[0, 0] * A[1, 2]) / d
+        out[2, 2] = (-A[0, 1] * A[1, 0] + A[0, 0] * A[1, 1]) / d
+    else:
+        out[0, 0], out[0, 1] = A[1, 1] / d, -A[0, 1] / d
+        out[1, 0], out[1, 1] = -A[1, 0] / d, A[0, 0] / d
+    return out
+
+
+def divu(u, v, _):                              # models/general.py:7-9
+    return div(u) * v
+
+
 def laplace(u, v, _):
     return dot(grad(u), grad(v))
 

@@ -137,6 +137,27 @@ def det(A):
     raise NotImplementedError
 
 
+def inv(A):
+    """Inverse over the two leading axes, cofactor / determinant entry by entry
+    in the reference's operation order (helpers.py:179-207)."""
+    detA = det(A)
+    if A.shape[0] == 3:
+        rows = [[(-A[1, 2] * A[2, 1] + A[1, 1] * A[2, 2]) / detA,
+                 (A[0, 2] * A[2, 1] - A[0, 1] * A[2, 2]) / detA,
+                 (-A[0, 2] * A[1, 1] + A[0, 1] * A[1, 2]) / detA],
+                [(A[1, 2] * A[2, 0] - A[1, 0] * A[2, 2]) / detA,
+                 (-A[0, 2] * A[2, 0] + A[0, 0] * A[2, 2]) / detA,
+                 (A[0, 2] * A[1, 0] - A[0, 0] * A[1, 2]) / detA],
+                [(-A[1, 1] * A[2, 0] + A[1, 0] * A[2, 1]) / detA,
+                 (A[0, 1] * A[2, 0] - A[0, 0] * A[2, 1]) / detA,
+                 (-A[0, 1] * A[1, 0] + A[0, 0] * A[1, 1]) / detA]]
+    elif A.shape[0] == 2:
+        rows = [[A[1, 1] / detA, -A[0, 1] / detA], [-A[1, 0] / detA, A[0, 0] / detA]]
+    else:
+        raise NotImplementedError
+    return np.stack([np.stack(r) for r in rows])
+
+
 def cross(A, B):
     if A.shape[0] == 2:
         return A[0] * B[1] - A[1] * B[0]
