@@ -17,7 +17,7 @@ from .mapping import MappingAffine, MappingIsoparametric
 from .dofs import Dofs
 from .quadrature import get_quadrature
 from .basis import AbstractBasis, CellBasis, Basis
-from .facet_basis import FacetBasis, BoundaryFacetBasis
+from .facet_basis import FacetBasis, BoundaryFacetBasis, InteriorFacetBasis
 from .field import DiscreteField, DeviceArray, asdevice
 from .form import (Form, BilinearForm, LinearForm, Functional, COOData, DeviceCSR,
                    FormExtraParams, asm)
@@ -33,7 +33,7 @@ __all__ = [
     "Element", "ElementH1", "ElementTriP1", "ElementTriP2", "ElementTetP1", "ElementTetP2",
     "ElementHex1", "ElementHex2", "ElementVector", "MappingAffine", "MappingIsoparametric",
     "Dofs", "get_quadrature", "AbstractBasis", "CellBasis", "Basis", "InteriorBasis",
-    "FacetBasis", "BoundaryFacetBasis",
+    "FacetBasis", "BoundaryFacetBasis", "InteriorFacetBasis",
     "DiscreteField", "DeviceArray", "asdevice", "Form", "BilinearForm", "LinearForm",
     "Functional", "COOData", "DeviceCSR", "FormExtraParams", "asm", "helpers", "models",
     "enforce", "condense", "solve", "solver_iter_pcg", "utils",

@@ -125,11 +125,23 @@ class CellBasis(AbstractBasis):
         return self.elem.ncomp
 
     def get_dofs(self, facets=None, elements=None, nodes=None, skip=None):
-        """Boundary DOFs (the no-argument form of the reference's
-        ``get_dofs``, abstract_basis.py:124-237)."""
-        if facets is not None or elements is not None or nodes is not None:
-            raise NotImplementedError("only get_dofs() without arguments (all boundary DOFs)")
-        return self.dofs.boundary()
+        """DOFs on a set of facets (abstract_basis.py:124-237): ``facets`` is None (the
+        whole boundary), an array of facet indices, a callable on facet midpoints, a
+        boundary name or a list of those; a dict of names gives a dict of results.
+        Returns the sorted array the reference's ``DofsView.all()`` would."""
+        if elements is not None or nodes is not None or skip is not None:
+            raise NotImplementedError("get_dofs: only the `facets` selector is supported")
+        if isinstance(facets, dict):
+            return {k: self.get_dofs(v) for k, v in facets.items()}
+        if facets is None:
+            return self.dofs.boundary()
+        return self.dofs.on_facets(self.mesh.normalize_facets(facets))
+
+    def with_element(self, elem):
+        """Same mesh, quadrature and element subset with another element
+        (cell_basis.py:262-275)."""
+        return type(self)(self.mesh, elem, mapping=self.mapping, quadrature=(self.X, self.W),
+                          elements=self.tind)
 
     def complement_dofs(self, *D):
         return np.setdiff1d(np.arange(self.N), np.concatenate([np.asarray(d).ravel() for d in D]))

@@ -71,12 +71,19 @@ class Dofs:
         # == max(element_dofs) + 1: every vertex/edge/facet/cell is referenced
         self.N = int(offset + self.interior_dofs.size)
 
+    def on_facets(self, facets):
+        """All DOFs attached to the vertices / edges / facets of the given facets,
+        sorted - what ``get_facet_dofs(facets).all()`` returns in the reference
+        (dofs.py:618-663, 90-107)."""
+        m = self.topo
+        facets = np.asarray(facets, dtype=np.int64)
+        out = [self.nodal_dofs[:, np.unique(m.facets[:, facets])].flatten()]
+        if self.edge_dofs.size:
+            out.append(self.edge_dofs[:, m.facet_edges(facets)].flatten())
+        if self.facet_dofs.size:
+            out.append(self.facet_dofs[:, facets].flatten())
+        return np.unique(np.concatenate(out)).astype(np.int32)
+
     def boundary(self):
         """All DOFs attached to boundary vertices / edges / facets."""
-        m = self.topo
-        out = [self.nodal_dofs[:, m.boundary_nodes()].flatten()]
-        if self.edge_dofs.size:
-            out.append(self.edge_dofs[:, m.boundary_edges()].flatten())
-        if self.facet_dofs.size:
-            out.append(self.facet_dofs[:, m.boundary_facets()].flatten())
-        return np.unique(np.concatenate(out)).astype(np.int32)
+        return self.on_facets(self.topo.boundary_facets())

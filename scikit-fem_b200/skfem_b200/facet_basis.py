@@ -83,6 +83,7 @@ class FacetBasis(CellBasis):
             self.find = np.nonzero(mesh.f2t[1] == -1)[0].astype(np.int32)
         else:
             self.find = np.asarray(mesh.normalize_facets(facets))
+        self._side = side
         self.tind = mesh.f2t[side, self.find]
         self.tind_normals = mesh.f2t[0, self.find]
         if len(self.find) == 0:
@@ -96,6 +97,11 @@ class FacetBasis(CellBasis):
         self._plans = {}
         self._fields = {}
         logger.info("Initializing finished.")
+
+    def with_element(self, elem):
+        """Same facets, side and quadrature with another element (facet_basis.py:257-270)."""
+        return type(self)(self.mesh, elem, mapping=self.mapping, quadrature=(self.X, self.W),
+                          facets=self.find, side=self._side)
 
     @property
     def nbs(self):
@@ -237,3 +243,16 @@ class FacetBasis(CellBasis):
 
 
 BoundaryFacetBasis = FacetBasis  # deprecated alias kept by the reference
+
+
+class InteriorFacetBasis(FacetBasis):
+    """FacetBasis over the interior facets by default; ``side`` selects which of
+    the two adjacent elements is traced
+    (skfem/assembly/basis/interior_facet_basis.py:12-50)."""
+
+    def __init__(self, mesh, elem, mapping=None, intorder=None, quadrature=None, facets=None,
+                 dofs=None, side=0, disable_doflocs=False):
+        if facets is None:
+            facets = np.nonzero(mesh.f2t[1] != -1)[0].astype(np.int32)
+        super().__init__(mesh, elem, mapping=mapping, intorder=intorder, quadrature=quadrature,
+                         facets=facets, dofs=dofs, side=side, disable_doflocs=disable_doflocs)

@@ -222,19 +222,22 @@ class Mesh:
     def boundary_nodes(self):
         return np.unique(self.facets[:, self.boundary_facets()])
 
-    def boundary_edges(self):
-        """Edges (3-D) lying on boundary facets."""
-        bf = self.facets[:, self.boundary_facets()]
+    def facet_edges(self, ix):
+        """Edges (3-D) lying on the facets ``ix`` - the reference's
+        ``np.unique(f2e[:, ix])`` (mesh.py:495-511)."""
+        bf = self.facets[:, np.asarray(ix, dtype=np.int64)]
         n = bf.shape[0]
+        # facet vertex loops: every consecutive pair is an edge (triangles: all
+        # three pairs; quads of a hex: the four sides)
         pairs = np.hstack([np.sort(bf[[a, (a + 1) % n]], axis=0) for a in range(n)])
-        if self.refdom is RefTet:
-            cand = pairs
-        else:  # quads of a hex: consecutive vertices along the facet loop
-            cand = pairs
         nv = self.nvertices
         key = self.edges[0].astype(np.int64) * nv + self.edges[1]
-        ckey = np.unique(cand[0].astype(np.int64) * nv + cand[1])
+        ckey = np.unique(pairs[0].astype(np.int64) * nv + pairs[1])
         return np.nonzero(np.isin(key, ckey))[0].astype(np.int32)
+
+    def boundary_edges(self):
+        """Edges (3-D) lying on boundary facets."""
+        return self.facet_edges(self.boundary_facets())
 
     boundaries = None  # optional {name: facet indices}
 
@@ -245,6 +248,20 @@ class Mesh:
         if boundaries_only:
             facets = np.intersect1d(facets, self.boundary_facets())
         return facets
+
+    def with_boundaries(self, boundaries, boundaries_only=True):
+        """Copy of the mesh with named boundaries: ``{name: facet indices | test on
+        facet midpoints}`` (mesh.py:791-830)."""
+        out = type(self)(self.doflocs, self.t)
+        named = dict(self.boundaries or {})
+        for name, spec in boundaries.items():
+            named[name] = (self.facets_satisfying(spec, boundaries_only=boundaries_only)
+                           if callable(spec) else np.asarray(spec, dtype=np.int32))
+        out.boundaries = named
+        for attr in ("_facets", "_t2f", "_edges", "_t2e", "_f2t", "_nvertices"):
+            if hasattr(self, attr):
+                setattr(out, attr, getattr(self, attr))
+        return out
 
     def normalize_facets(self, facets):
         """Array of facet indices from an index, an array, a list of criteria,

@@ -103,6 +103,35 @@ def test_facet_basis_host_side_matches_reference(name, M, E):
         m.normalize_facets("left")
 
 
+@pytest.mark.parametrize("name,M,E,args", [
+    ("tri_p2", "MeshTri", "ElementTriP2", None), ("tet_p2", "MeshTet", "ElementTetP2", 3),
+    ("tet_vp1", "MeshTet", "ElementTetP1", 3), ("hex2", "MeshHex", "ElementHex2", 3)])
+def test_get_dofs_facet_selectors_match_reference(name, M, E, args):
+    """get_dofs(): whole boundary, named boundaries (with_boundaries), a set of
+    names, a test on facet midpoints - against basis.get_dofs(...).all() of the
+    reference (tests/golden/bc_get_dofs.npz, tools/gen_golden_bc.py)."""
+    g = load("bc_get_dofs")
+    if args is None:
+        m = fem.MeshTri().refined(2)
+    else:
+        xs = np.linspace(0, 1, 4)
+        m = getattr(fem, M).init_tensor(xs, xs, xs)
+    m = m.with_boundaries({'left': lambda x: np.isclose(x[0], 0.),
+                           'top': lambda x: np.isclose(x[1], 1.)})
+    e = getattr(fem, E)()
+    if name == "tet_vp1":
+        e = fem.ElementVector(e)
+    basis = fem.Basis(m, e)
+    assert np.array_equal(m.boundaries['left'], g[name + "_left_facets"])
+    assert np.array_equal(m.boundaries['top'], g[name + "_top_facets"])
+    assert np.array_equal(basis.get_dofs(), g[name + "_all"])
+    assert np.array_equal(basis.get_dofs('left'), g[name + "_left"])
+    assert np.array_equal(basis.get_dofs({'left', 'top'}), g[name + "_both"])
+    assert np.array_equal(basis.get_dofs(lambda x: x[0] > 0.6), g[name + "_fn"])
+    with pytest.raises(ValueError, match="not found"):
+        basis.get_dofs('bottom')
+
+
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "skfem_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)

@@ -62,3 +62,27 @@ mx = fem.MeshTet.init_tensor(xs, xs, np.linspace(0, 1, 3))
 q = mx.p.copy()
 q[0] = mx.p[0] + 0.03 * np.sin(7 * mx.p[1])
 dump("bc_tet_p2", fem.MeshTet(q, mx.t), fem.ElementTetP2())
+
+
+# ---- get_dofs with facet selectors (abstract_basis.py:124-237) -----------------------
+def dofs_case(m, e):
+    mb = m.with_boundaries({'left': lambda x: np.isclose(x[0], 0.),
+                            'top': lambda x: np.isclose(x[1], 1.)})
+    basis = fem.Basis(mb, e)
+    return dict(all=basis.get_dofs().all(), left=basis.get_dofs('left').all(),
+                both=basis.get_dofs({'left', 'top'}).all(),
+                fn=basis.get_dofs(lambda x: x[0] > 0.6).all(),
+                left_facets=mb.boundaries['left'], top_facets=mb.boundaries['top'])
+
+
+out = {}
+xs3 = np.linspace(0, 1, 4)
+for name, m, e in [("tri_p2", fem.MeshTri().refined(2), fem.ElementTriP2()),
+                   ("tet_p2", fem.MeshTet.init_tensor(xs3, xs3, xs3), fem.ElementTetP2()),
+                   ("tet_vp1", fem.MeshTet.init_tensor(xs3, xs3, xs3),
+                    fem.ElementVector(fem.ElementTetP1())),
+                   ("hex2", fem.MeshHex.init_tensor(xs3, xs3, xs3), fem.ElementHex2())]:
+    for k, v in dofs_case(m, e).items():
+        out[name + "_" + k] = v
+np.savez_compressed(os.path.join(OUT, "bc_get_dofs.npz"), **out)
+print("bc_get_dofs", sorted(out)[:4], "...")
