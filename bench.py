@@ -178,7 +178,8 @@ def run_gpu(args):
         # step i+1 (two output buffer sets); SKB_PIPELINE=0 serialises them again
         da = DistributedAssembler(laplace, basis, l2g, Nglob, ranges, reuse_buffers=True,
                                   graph_exchange=os.environ.get("SKB_GRAPH_EXCHANGE") == "1",
-                                  pipeline=os.environ.get("SKB_PIPELINE", "1") == "1")
+                                  pipeline=os.environ.get("SKB_PIPELINE", "1") == "1",
+                                  sm_reserve=int(os.environ.get("SKB_SM_RESERVE", "0")))
         A = da.assemble()
     torch.cuda.synchronize()
     cold_ms = 1e3 * (time.perf_counter() - t0)

@@ -10,7 +10,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
  *   - the caller owns and allocates every buffer (inputs, outputs, scratch);
- *     nothing is retained between calls, the library holds no global state;
+ *     nothing is retained between calls; the only process-wide state is the
+ *     launch counter, the profiling switches and the skb_sm_reserve knob;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
  *     calls return without synchronising unless documented otherwise;
  *   - return value: 0 on success, a positive cudaError_t, or a negative
@@ -230,6 +231,12 @@ int skb_csr_condense_fill(const int32_t *indptr, const int32_t *indices, const d
 /* y = A x with the row sums in scipy's csr_matvec order (hand-off to solvers) */
 int skb_csr_spmv(const int32_t *indptr, const int32_t *indices, const double *data,
                  const double *x, double *y, int64_t nrows, void *stream);
+
+/* Tuning knob (process-wide, default 0): the persistent fused kernel sizes its
+ * grid for (SM count - sms) SMs, leaving room for kernels of other streams - the
+ * NCCL all-to-all of the multi-GPU path, which otherwise cannot start before the
+ * fused kernel of the next step has drained.                                   */
+void skb_sm_reserve(int sms);
 
 /* number of kernels of this library launched so far by this process (the
  * bench's `gpu_launches`); reset != 0 zeroes the counter after reading.     */

@@ -29,6 +29,9 @@ void count_launch(int n = 1);
 // bit1 skips P2, bit2 prints per-role cycle counts, bit3 forces the dense
 // (uncached) element-local kernel
 int debug_flags();
+// SMs the persistent fused kernel leaves free (skb_sm_reserve): room for a
+// concurrent NCCL kernel when the interface exchange overlaps the next step
+int sm_reserve();
 
 // ---------------------------------------------------------------------------
 // Correctly rounded a/b for many numerators sharing one denominator.

@@ -367,7 +367,9 @@ static int launch_fused(const P1Args &a, size_t smem, int sms, bool q4, cudaStre
   const int by_threads = 2048 / (TT + NRED + 32);
   if (per_sm > by_threads) per_sm = by_threads;
   if (per_sm < 1) per_sm = 1;
-  const int cap = per_sm * sms;
+  int free_sms = sm_reserve();
+  if (free_sms > sms - 1) free_sms = sms - 1;
+  const int cap = per_sm * (sms - free_sms);
   const int grid = a.ntiles < cap ? a.ntiles : cap;
   if (q4) {
     auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, true>;

@@ -18,6 +18,8 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_debug{0};
 int debug_flags() { return g_debug.load(std::memory_order_relaxed); }
+static std::atomic<int> g_sm_reserve{0};
+int sm_reserve() { return g_sm_reserve.load(std::memory_order_relaxed); }
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
@@ -187,5 +189,7 @@ extern "C" int64_t skb_launch_count(int reset) {
 }
 
 extern "C" void skb_debug_flags(int flags) { skb::g_debug.store(flags); }
+
+extern "C" void skb_sm_reserve(int sms) { skb::g_sm_reserve.store(sms < 0 ? 0 : sms); }
 
 extern "C" const char *skb_version(void) { return "skfem_b200 0.1 (sm_100a, fmad=off)"; }

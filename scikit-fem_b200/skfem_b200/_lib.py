@@ -51,6 +51,7 @@ SIGNATURES = {
                                        _I32, C.c_double, _I32, _P, _P, _P]),
     "skb_p1_fused_smem_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "skb_debug_flags": (None, [_INT]),
+    "skb_sm_reserve": (None, [_INT]),
     "skb_p1_combine": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "skb_facet_geometry": (_INT, [_SP, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I32,
                                   _P, _P, _P, _P, _P, _P]),

@@ -32,6 +32,11 @@ from __future__ import annotations
 import numpy as np
 
 
+def _lib():
+    from . import _lib as L
+    return L.lib()
+
+
 def _torch():
     import torch
     return torch
@@ -211,7 +216,7 @@ class DistributedAssembler:
     """
 
     def __init__(self, form, basis, l2g, N, ranges=None, group=None, reuse_buffers=False,
-                 graph_exchange=False, pipeline=False):
+                 graph_exchange=False, pipeline=False, sm_reserve=0):
         # graph_exchange=True also captures the NCCL all-to-all in the CUDA graph; it hung
         # on the B200 box with torch 2.11 / NCCL 2.28 (round 1), so it is opt-in.
         import torch.distributed as dist
@@ -224,6 +229,9 @@ class DistributedAssembler:
         # carries the event that completes it (DistributedCSR.wait) and is
         # overwritten two calls later.
         self.pipeline = bool(pipeline) and self.reuse_buffers
+        # sm_reserve (pipelined mode): SMs the persistent fused kernel leaves free so
+        # that the NCCL kernel of the previous step's exchange can run beside it
+        self.sm_reserve = int(sm_reserve)
         self._sets = None
         self._graph = self._out = self._data = None
         self._graph_has_exchange = False
@@ -300,10 +308,14 @@ class DistributedAssembler:
                 ex.finish(out)                                                         # NCCL warm
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    if ex.unwritten.numel():
-                        out[:ex.nnz].index_fill_(0, ex.unwritten, 0.0)
-                    self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
+                _lib().skb_sm_reserve(self.sm_reserve)      # grid size is baked into the graph
+                try:
+                    with torch.cuda.graph(g):
+                        if ex.unwritten.numel():
+                            out[:ex.nnz].index_fill_(0, ex.unwritten, 0.0)
+                        self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)
+                finally:
+                    _lib().skb_sm_reserve(0)
                 self._sets.append({"out": out, "graph": g,
                                    "computed": torch.cuda.Event(), "done": torch.cuda.Event()})
         st = self._sets[self._flip]
