@@ -202,6 +202,17 @@ class DistributedCSR:
         from scipy.sparse import csr_matrix
         nrows = int(self.indptr.shape[0]) - 1
         self.wait()
+        if self.data.is_cuda:          # pinned staging, three overlapping async copies
+            torch = _torch()
+
+            def d2h(t):
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h.copy_(t, non_blocking=True)
+                return h
+            hd, hi, hp = d2h(self.data), d2h(self.indices), d2h(self.indptr)
+            torch.cuda.current_stream().synchronize()
+            return csr_matrix((hd.numpy(), hi.numpy(), hp.numpy()), shape=(nrows, self.shape[1]),
+                              copy=False)
         return csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
                            self.indptr.cpu().numpy()), shape=(nrows, self.shape[1]))
 
