@@ -154,7 +154,8 @@ def run_gpu(args):
 
     from skfem_b200 import form as _form
     _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads,
-                      fused_ring=args.ring)
+                      fused_ring=args.ring, fused_arith=args.arith,
+                      fused_spread=not args.no_spread)
     cells = args.cells
     da = None
     if world == 1:
@@ -254,6 +255,31 @@ def run_gpu(args):
     ms_step = ms / args.steps
     value = nel * world / (ms_step * 1e-3)
 
+    # side measurement (not the headline): the same warm step with the fused kernel's
+    # opt-in fast arithmetic (FMA + one reciprocal per element, values within rtol 1e-12)
+    fast_line = None
+    if world == 1 and graph is not None and args.arith == "exact" and not args.no_fused:
+        _form.set_options(fused_arith="fast")
+        try:
+            step_eager()
+            torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                step_eager()
+            for _ in range(3):
+                g2.replay()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                g2.replay()
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / args.steps
+            fast_line = {"ms_per_step": fms, "value": nel / (fms * 1e-3), "unit": "elements/s",
+                         "note": "opt-in set_options(fused_arith='fast'); not the headline"}
+        finally:
+            _form.set_options(fused_arith="exact")
+
     # ---- end to end: host buffers in, scipy CSR out, through the public API ----
     e2e = None
     if not args.no_e2e:
@@ -346,6 +372,8 @@ def run_gpu(args):
                              "t + p + CSR data"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
+    if fast_line is not None:
+        line["fast_arith"] = fast_line
     if world == 1 and not args.no_cpu:
         cores = 1
         dt, cnel, cnnz = cpu_assemble(args.ref_cells, 0)
@@ -376,6 +404,11 @@ def main():
                     help="launch the warm step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-fused", action="store_true", dest="no_fused",
                     help="time the generic two-kernel path instead of the fused P1 kernel")
+    ap.add_argument("--arith", default="exact", choices=["exact", "fast"],
+                    help="fused-kernel arithmetic: exact = reference operation order (default, "
+                         "the headline), fast = FMA + reciprocal (values within rtol 1e-12)")
+    ap.add_argument("--no-spread", action="store_true", dest="no_spread",
+                    help="keep the COO order inside the P2 lists (no plan-time bank spreading)")
     ap.add_argument("--tile", type=int, default=512)
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--threads", type=int, default=480,

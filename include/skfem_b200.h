@@ -147,7 +147,11 @@ int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *se
  * needs (must be <= 227 KB).  tame != 0 asserts that every vertex coordinate is
  * 0 or within [2^-60, 2^60] in magnitude, which lets the kernel use its
  * shared-reciprocal exact division without per-element range checks (tame == 0
- * selects plain IEEE division).  w = the common quadrature weight (all weights of
+ * selects plain IEEE division).  tame == 2 (opt-in, tile 512 / 480 reduce threads)
+ * selects the fast arithmetic: fused multiply-adds and one reciprocal per element,
+ * values within a few ulp per term of the reference order (inside the rtol 1e-12
+ * bar for CSR values; element-local data no longer bit-identical).
+ * w = the common quadrature weight (all weights of
  * the rule must be equal), nqp = number of quadrature points.  skb_p1_combine
  * adds, in tile order, the per-tile partial sums of CSR slots touched by more
  * than one tile.  No float atomics: bit-reproducible.                        */
@@ -231,6 +235,17 @@ int skb_csr_condense_fill(const int32_t *indptr, const int32_t *indices, const d
 /* y = A x with the row sums in scipy's csr_matvec order (hand-off to solvers) */
 int skb_csr_spmv(const int32_t *indptr, const int32_t *indices, const double *data,
                  const double *x, double *y, int64_t nrows, void *stream);
+
+/* Plan-time pass over the records' sliced-ELL index sections (the order in which
+ * a CSR slot's triplets are added is unspecified in the reference, coo_data.py:
+ * 34-36 -> scipy tocsr; it only has to be fixed): for each of the `ngroups`
+ * 32-lane groups, whose len = grp_len[g] columns of 32 uint16 staging indices
+ * start at rec16 + grp_pos[g], permute every lane's terms over the columns so that
+ * each half-warp column touches every shared-memory bank pair at most
+ * ceil(degree/len) times (bipartite edge colouring), and point unused cells at
+ * the staged zero zero_base + b of the least loaded bank pair b.  In place.    */
+int skb_p1_plan_spread(uint16_t *rec16, const int64_t *grp_pos, const int32_t *grp_len,
+                       int64_t ngroups, int32_t zero_base, void *stream);
 
 /* Tuning knob (process-wide, default 0): the persistent fused kernel sizes its
  * grid for (SM count - sms) SMs, leaving room for kernels of other streams - the

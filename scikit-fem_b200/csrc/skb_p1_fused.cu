@@ -134,12 +134,20 @@ __device__ __forceinline__ void fence_proxy_async() {
 // vertex gather of tile k+2 and retire the gather of tile k+1; one block
 // barrier per iteration, then one thread re-arms the freed record buffer with
 // the TMA fetch of tile k-1+NR.
-template <int T_ELEMS, int NRED, int NR, bool NQP4>
-__global__ void __launch_bounds__(T_ELEMS + NRED + 32)
+// FAST (opt-in, P1Args::tame == 2): the element arithmetic uses fused multiply-adds
+// and one reciprocal instead of the reference's operation order - ~100 instead of
+// ~190 FP64 instructions per element.  Values then agree with the reference to a few
+// ulp per term (well inside the rtol 1e-12 bar for CSR values) but the element-local
+// data is no longer bit-identical; the sparsity pattern is unaffected (it comes from
+// the plan, which is always built from bit-exact local data).
+// CT = compute threads (default one per element); CT < T_ELEMS lets every compute thread
+// take T_ELEMS / CT elements in turn and frees thread slots for reduce warps.
+template <int T_ELEMS, int NRED, int NR, bool NQP4, bool FAST = false, int CT = T_ELEMS>
+__global__ void __launch_bounds__(CT + NRED + 32)
 p1tet_laplace_fused_kernel(const P1Args a) {
   static_assert(NR >= 4, "record ring must hold tiles k-1 .. k+2");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int VSTRIDE = 10 * T_ELEMS + 2;
+  constexpr int VSTRIDE = 10 * T_ELEMS + 16;   // + one staged 0.0 per bank pair
   // shared layout: vals[2] | coords[3] | records[NR] | mbarriers | flags | counters
   double *vals = reinterpret_cast<double *>(smem_raw);                      // [2][VSTRIDE]
   // coordinates: 3 buffers x {x[vcap], y[vcap], z[vcap]} (struct of arrays: a
@@ -148,10 +156,11 @@ p1tet_laplace_fused_kernel(const P1Args a) {
   unsigned char *recs = reinterpret_cast<unsigned char *>(coords + 9 * (size_t)a.vcap);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(recs + (size_t)NR * a.rec_cap);
   // roles: [0, T) compute, [T, T+NRED) reduce, last warp = TMA producer (lane 0)
-  const bool is_compute = threadIdx.x < T_ELEMS;
-  const bool is_reduce = !is_compute && threadIdx.x < T_ELEMS + NRED;
-  const bool is_producer = threadIdx.x == T_ELEMS + NRED;
-  const int rtid = (int)threadIdx.x - T_ELEMS;        // reduce-thread index
+  static_assert(T_ELEMS % CT == 0, "elements per compute thread must be integral");
+  const bool is_compute = threadIdx.x < CT;
+  const bool is_reduce = !is_compute && threadIdx.x < CT + NRED;
+  const bool is_producer = threadIdx.x == CT + NRED;
+  const int rtid = (int)threadIdx.x - CT;             // reduce-thread index
   const int lane = threadIdx.x & 31;
   const int rwarp = rtid >> 5;                        // reduce-warp index
   constexpr int NRW = NRED / 32;
@@ -197,8 +206,10 @@ p1tet_laplace_fused_kernel(const P1Args a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NR; ++i) mbar_init(&mbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    vals[10 * T_ELEMS] = 0.0;
-    vals[VSTRIDE + 10 * T_ELEMS] = 0.0;
+    for (int i = 0; i < 16; ++i) {
+      vals[10 * T_ELEMS + i] = 0.0;
+      vals[VSTRIDE + 10 * T_ELEMS + i] = 0.0;
+    }
   }
   __syncthreads();
   if (nk <= 0) return;
@@ -219,7 +230,7 @@ p1tet_laplace_fused_kernel(const P1Args a) {
 
   // profiling aid (debug bit 2): cycles block 0 spends working vs at the barrier
   const bool timing = (a.debug & 4) && blockIdx.x == 0 && lane == 0 &&
-                      (threadIdx.x == 0 || threadIdx.x == T_ELEMS);
+                      (threadIdx.x == 0 || threadIdx.x == CT);
   long long t_work = 0, t_bar = 0, t_mark = timing ? clock64() : 0;
   for (int k = 0; k <= nk; ++k) {
     if (is_compute) {
@@ -231,7 +242,8 @@ p1tet_laplace_fused_kernel(const P1Args a) {
         const double *sx = coords + (size_t)(k % 3) * 3 * a.vcap, *sy = sx + a.vcap,
                      *sz = sy + a.vcap;
         double *out = vals + (size_t)(k & 1) * VSTRIDE;
-        const int el = threadIdx.x;
+#pragma unroll 1
+        for (int el = threadIdx.x; el < T_ELEMS; el += CT) {
         const ushort4 v = tl[el];
         if (v.x != 0xFFFF) {  // not a padding element of the last tile
           double A[3][3];
@@ -241,10 +253,30 @@ p1tet_laplace_fused_kernel(const P1Args a) {
             A[1][0] = sy[v.y] - y0; A[1][1] = sy[v.z] - y0; A[1][2] = sy[v.w] - y0;
             A[2][0] = sz[v.y] - z0; A[2][1] = sz[v.z] - z0; A[2][2] = sz[v.w] - z0;
           }
-          const double det = det3(A);
-          double n[3][3], inv[3][3];
-          cofactors3(A, n);
-          if (tame && det != 0.0) {
+          double det, n[3][3], inv[3][3];
+          if (FAST) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {   // cofactors, same sign convention as cofactors3
+              const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                n[j][i] = __fma_rn(A[i1][j1], A[i2][j2], -(A[i1][j2] * A[i2][j1]));
+              }
+            }
+            det = __fma_rn(A[0][0], n[0][0], __fma_rn(A[0][1], n[1][0], A[0][2] * n[2][0]));
+            const double y = 1.0 / det;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) inv[i][j] = n[i][j] * y;
+          } else {
+            det = det3(A);
+            cofactors3(A, n);
+          }
+          if (FAST) {
+            // inverse already formed above
+          } else if (tame && det != 0.0) {
             const double y = __drcp_rn(det);
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -267,13 +299,21 @@ p1tet_laplace_fused_kernel(const P1Args a) {
             g[3][j] = inv[2][j];
           }
           const double dx = fabs(det) * a.w;  // cell_basis.py:104-105
+          const double dxs = dx * (double)a.nqp;   // FAST: nqp equal terms = one product
 #pragma unroll
           for (int p = 0; p < 4; ++p)
 #pragma unroll
             for (int q = p; q < 4; ++q) {
-              const double d = (g[p][0] * g[q][0] + g[p][1] * g[q][1]) + g[p][2] * g[q][2];
-              out[sym_index4(p, q) * T_ELEMS + el] = sum_equal_terms<NQP4>(d * dx, a.nqp);
+              if (FAST) {
+                const double d = __fma_rn(g[p][2], g[q][2],
+                                          __fma_rn(g[p][1], g[q][1], g[p][0] * g[q][0]));
+                out[sym_index4(p, q) * T_ELEMS + el] = d * dxs;
+              } else {
+                const double d = (g[p][0] * g[q][0] + g[p][1] * g[q][1]) + g[p][2] * g[q][2];
+                out[sym_index4(p, q) * T_ELEMS + el] = sum_equal_terms<NQP4>(d * dx, a.nqp);
+              }
             }
+        }
         }
       }
     } else if (is_reduce) {
@@ -359,26 +399,31 @@ p1_combine_kernel(const double *__restrict__ scratch, const uint32_t *__restrict
   }
 }
 
-template <int TT, int NRED, int NR>
+template <int TT, int NRED, int NR, int CT = TT>
 static int launch_fused(const P1Args &a, size_t smem, int sms, bool q4, cudaStream_t st) {
   // persistent grid: as many CTAs per SM as shared memory, threads and
   // registers (<= 64 per thread by __launch_bounds__) allow
   int per_sm = (int)((228 * 1024) / (smem + 1024));
-  const int by_threads = 2048 / (TT + NRED + 32);
+  const int by_threads = 2048 / (CT + NRED + 32);
   if (per_sm > by_threads) per_sm = by_threads;
   if (per_sm < 1) per_sm = 1;
   int free_sms = sm_reserve();
   if (free_sms > sms - 1) free_sms = sms - 1;
   const int cap = per_sm * (sms - free_sms);
   const int grid = a.ntiles < cap ? a.ntiles : cap;
-  if (q4) {
-    auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, true>;
+  constexpr bool kHasFast = TT == 512 && (NRED == 480 || CT != TT);   // fast arithmetic variants
+  if (a.tame == 2 && kHasFast) {
+    auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, true, kHasFast, CT>;
     SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, TT + NRED + 32, smem, st>>>(a);
+    k<<<grid, CT + NRED + 32, smem, st>>>(a);
+  } else if (q4) {
+    auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, true, false, CT>;
+    SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, CT + NRED + 32, smem, st>>>(a);
   } else {
-    auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, false>;
+    auto k = p1tet_laplace_fused_kernel<TT, NRED, NR, false, false, CT>;
     SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, TT + NRED + 32, smem, st>>>(a);
+    k<<<grid, CT + NRED + 32, smem, st>>>(a);
   }
   return (int)cudaGetLastError();
 }
@@ -387,7 +432,7 @@ static int launch_fused(const P1Args &a, size_t smem, int sms, bool q4, cudaStre
 
 extern "C" int64_t skb_p1_fused_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap,
                                            int32_t vcap) {
-  return (int64_t)(sizeof(double) * 2 * (10 * (size_t)tile_elems + 2) + 9 * (size_t)vcap * 8 +
+  return (int64_t)(sizeof(double) * 2 * (10 * (size_t)tile_elems + 16) + 9 * (size_t)vcap * 8 +
                    (size_t)ring * rec_cap + 8 * (size_t)ring + 32);
 }
 
@@ -430,6 +475,16 @@ extern "C" int skb_p1tet_laplace_fused(const double *p, int64_t npts, const void
   SKB_P1_CASE(512, 480)
   SKB_P1_CASE(768, 224)
 #undef SKB_P1_CASE
+  // two elements per compute thread (256 compute threads), more reduce warps
+#define SKB_P1_CASE2(TT, NRED, CT)                                                 \
+  if (tile_elems == TT && reduce_threads == NRED) {                                \
+    if (ring == 4) rc = launch_fused<TT, NRED, 4, CT>(a, smem, sms, q4, st);       \
+    else if (ring == 5) rc = launch_fused<TT, NRED, 5, CT>(a, smem, sms, q4, st);  \
+  }
+  SKB_P1_CASE2(512, 736, 256)
+  SKB_P1_CASE2(512, 608, 256)
+  SKB_P1_CASE2(512, 640, 128)
+#undef SKB_P1_CASE2
   if (rc == SKB_OK) count_launch();
   return rc;
 }

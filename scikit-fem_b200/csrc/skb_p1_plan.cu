@@ -1,9 +1,3 @@
-// EXPERIMENT (not built into libskfem_b200.so): see profiles/r1_fused_experiments.md.
-// Reduced the P2 gather wavefronts from 5.5 to 3.6 per LDS.64 without reducing the
-// step time; kept for round 2.  To try it again: move to scikit-fem_b200/csrc/, declare
-// skb_p1_plan_spread in include/skfem_b200.h and _lib.py, give the fused kernel 16
-// staged zeros (VSTRIDE = 10*T + 16) and call it at the end of fused.build().
-//
 // Plan-time helper of the fused P1 path: bank-conflict-free ordering of the
 // sliced-ELL staging indices.
 //

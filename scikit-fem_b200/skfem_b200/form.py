@@ -44,7 +44,11 @@ def _torch():
     return torch
 
 
-_CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring": 4}
+# fused_arith: "exact" (reference operation order, bit-identical local data) or "fast"
+# (fused multiply-adds + one reciprocal in the warm fused kernel: values within a few
+# ulp per term, i.e. inside the rtol 1e-12 bar, pattern unchanged)
+_CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring": 4,
+           "fused_arith": "exact", "fused_spread": True}
 
 
 def set_options(**kw):
@@ -441,12 +445,13 @@ class BilinearForm(Form):
                 if fp is False:
                     fp = fused.build_auto(ubasis, plan, T=fused_tile(),
                                           threads=int(_CONFIG["fused_threads"]),
-                                          ring=int(_CONFIG["fused_ring"]), slot_map=slot_map)
+                                          ring=int(_CONFIG["fused_ring"]), slot_map=slot_map,
+                                          spread=bool(_CONFIG["fused_spread"]))
                     ubasis._plans[fkey] = fp      # None: tiles too big, stay generic
                 if fp is not None:
                     data = out if out is not None else torch.empty(
                         plan.nnz, dtype=torch.float64, device=fp.p.device)
-                    fused.run(fp, data, _stream())
+                    fused.run(fp, data, _stream(), fast=_CONFIG["fused_arith"] == "fast")
                     return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
         local = self._local(ubasis, vbasis, **kwargs)
         if plan is None:

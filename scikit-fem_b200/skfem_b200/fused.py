@@ -75,7 +75,7 @@ def applicable(basis, form):
     return bool(np.all(W == W[0]))
 
 
-def build(basis, plan, T=512, threads=480, ring=4, slot_map=None):
+def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
     """``slot_map`` (optional int64 tensor, CSR slot -> output index): targets
     written by the kernels are remapped through it (multi-GPU direct write)."""
     torch = _torch()
@@ -292,6 +292,16 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None):
     cpos = ((rs[t_of] + off_ids[t_of]) // 2 + grp_base[g_of] + (kth - sub * chunk[s_new]) * 32
             + lane_of_slot[s_new] + sub)
     buf16[cpos] = sid.to(torch.int16)
+    # reorder every lane's terms over the columns so that each LDS.64 of P2 is
+    # spread over the shared-memory banks (csrc/skb_p1_plan.cu)
+    if spread and dev.type == "cuda" and ngroups:
+        grp_pos = ((rs[grp_tile] + off_ids[grp_tile]) // 2 + grp_base).contiguous()
+        glen32 = grp_len.to(torch.int32).contiguous()
+        code = _lib.lib().skb_p1_plan_spread(
+            buf16.data_ptr(), grp_pos.data_ptr(), glen32.data_ptr(), ngroups, zero_idx,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(code, "skb_p1_plan_spread")
+        torch.cuda.current_stream().synchronize()     # grp_pos / glen32 die here
     fp.rec = buf32
     fp.rec_start = rec_start.contiguous()            # int64 == uint64 for the kernel
     fp.nts, fp.ncontrib, fp.ncontrib_sell, fp.ngroups = nts, ncontrib, ncontrib_sell, ngroups
@@ -315,7 +325,7 @@ class FusedPlanTooBig(RuntimeError):
     pass
 
 
-def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None):
+def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
     """Build with the requested tile, halving it while the tile's record ring
     and coordinates do not fit in shared memory (irregular meshes whose tiles
     touch many vertices).  Returns None if even the smallest tile is too big:
@@ -324,18 +334,21 @@ def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None):
                                 if c[0] < T]
     for tile, thr in options:
         try:
-            return build(basis, plan, T=tile, threads=thr, ring=ring, slot_map=slot_map)
+            return build(basis, plan, T=tile, threads=thr, ring=ring, slot_map=slot_map,
+                         spread=spread)
         except FusedPlanTooBig:
             continue
     return None
 
 
-def run(fp, data, stream):
-    """Warm numeric phase: two kernel launches, nothing else."""
+def run(fp, data, stream, fast=False):
+    """Warm numeric phase: two kernel launches, nothing else.  ``fast``: fused
+    multiply-add arithmetic in the element kernel (see csrc/skb_p1_fused.cu, FAST)."""
     lib = _lib.lib()
     code = lib.skb_p1tet_laplace_fused(
         fp.p.data_ptr(), fp.p.shape[1], fp.rec.data_ptr(), fp.rec_start.data_ptr(), fp.ntiles,
-        fp.T, fp.threads, fp.ring, fp.rec_cap, fp.vcap, fp.tame, C.c_double(fp.w), fp.nqp,
+        fp.T, fp.threads, fp.ring, fp.rec_cap, fp.vcap, 2 if fast else fp.tame, C.c_double(fp.w),
+        fp.nqp,
         data.data_ptr(), fp.scratch.data_ptr(), stream)
     _lib.check(code, "skb_p1tet_laplace_fused")
     code = lib.skb_p1_combine(fp.scratch.data_ptr(), fp.sptr.data_ptr(), fp.gslot.data_ptr(),

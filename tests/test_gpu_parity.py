@@ -329,3 +329,38 @@ def test_device_topology_matches_reference_numbering():
     fh, t2fh = O.facets_of(oh)
     got_f, got_t2f = _build_entities_device(mh.t, mh.refdom.facets, int(mh.t.max()) + 1, False)
     assert np.array_equal(got_f, fh) and np.array_equal(got_t2f, t2fh)
+
+
+def test_fused_fast_arithmetic_within_tolerance():
+    """Opt-in fast arithmetic of the fused kernel (FMA + one reciprocal per element):
+    same pattern, CSR values within the rtol 1e-12 bar of the oracle, and still
+    bit-identical from run to run."""
+    from oracle import skfem_oracle as O
+    from skfem_b200.form import set_options
+    from skfem_b200.models.poisson import laplace
+    rng = np.random.default_rng(5)
+    x = np.sort(np.r_[0., rng.uniform(0.05, 0.95, 10), 1.])
+    y = np.sort(np.r_[0., rng.uniform(0.05, 0.95, 9), 1.])
+    z = np.linspace(0, 1, 12)
+    m = fem.MeshTet.init_tensor(x, y, z)
+    q = m.p.copy()
+    q[0] = m.p[0] + 0.03 * np.sin(7 * m.p[1])
+    q[1] = m.p[1] + 0.02 * m.p[2] ** 2
+    m = fem.MeshTet(q, m.t)
+    om = mesh_of(dict(p=m.p, t=m.t), "tet")
+    ref = O.assemble_bilinear(O.laplace, O.cell_basis(om, O.element("tet_p1")))
+    b = fem.Basis(m, fem.ElementTetP1())
+    try:
+        set_options(fused_arith="fast")
+        laplace.assemble(b)                       # cold (always exact: builds the plan)
+        A1 = laplace.assemble(b)                  # warm: fused kernel, fast arithmetic
+        A2 = laplace.assemble(b)
+    finally:
+        set_options(fused_arith="exact")
+    A3 = laplace.assemble(b)                      # warm, exact arithmetic
+    assert np.array_equal(A1.indptr, ref.indptr) and np.array_equal(A1.indices, ref.indices)
+    assert np.array_equal(A1.data, A2.data)
+    scale = np.abs(ref.data).max()
+    np.testing.assert_allclose(A1.data, ref.data, rtol=1e-12, atol=1e-12 * scale)
+    np.testing.assert_allclose(A3.data, ref.data, rtol=1e-12, atol=1e-12 * scale)
+    print("fast vs exact max rel diff", np.abs(A1.data - A3.data).max() / scale)

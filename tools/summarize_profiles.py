@@ -15,22 +15,38 @@ G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
-# 1. launch list -> per-kernel average duration and share of the step
+# 1. launch list -> per-kernel average duration and share, warm step and one-time work apart
 src = os.path.join(G, "launches_%s.csv" % tag)
 if os.path.exists(src):
     lines = [l for l in open(src) if not l.startswith("==")]
-    agg = collections.OrderedDict()
-    for row in csv.DictReader(lines):
-        agg.setdefault(row["Kernel Name"], []).append(float(row["Metric Value"].replace(",", "")))
-    tot = sum(sum(v) for v in agg.values())
+    rows = [(r["Kernel Name"], float(r["Metric Value"].replace(",", "")))
+            for r in csv.DictReader(lines)]
+    first = next((i for i, (n, _) in enumerate(rows) if "p1tet_laplace_fused" in n), len(rows))
+
+    def table(f, part):
+        agg = collections.OrderedDict()
+        for n, v in part:
+            agg.setdefault(n, []).append(v)
+        tot = sum(sum(v) for v in agg.values()) or 1.0
+        f.write("| kernel | launches | avg us | share of listed time |\n|---|---|---|---|\n")
+        for k, v in agg.items():
+            f.write("| `%s` | %d | %.1f | %.1f %% |\n" % (k[:110], len(v), sum(v) / len(v) / 1e3,
+                                                         100 * sum(v) / tot))
+        return tot
+
     with open(os.path.join(P, "%s_launches.md" % tag), "w") as f:
         f.write("# ncu launch list (%s): `ncu --metrics gpu__time_duration.sum --clock-control none`\n\n"
-                "Command: `python bench.py --steps 5 --warmup 3 --no-cpu --no-graph` (1 GPU). "
-                "Durations are cold-cache and serialised under ncu; compare shares.\n\n"
-                "| kernel | launches | avg us | share of listed time |\n|---|---|---|---|\n" % tag)
-        for k, v in agg.items():
-            f.write("| `%s` | %d | %.1f | %.1f %% |\n" % (k[:90], len(v), sum(v) / len(v) / 1e3,
-                                                         100 * sum(v) / tot))
+                "Command: `python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-graph` (1 GPU, "
+                "%d launches in total). Durations are cold-cache and serialised under ncu; compare "
+                "shares.\n\n## Warm step (the timed region: every launch from the first fused "
+                "launch on)\n\n" % (tag, len(rows)))
+        table(f, rows[first:])
+        lib = [(n, v) for n, v in rows[:first] if "skb::" in n]
+        other = [("torch / CUB kernels of the cold plan build and the fused-plan build "
+                  "(sort, unique, searchsorted, index ops)", v) for n, v in rows[:first]
+                 if "skb::" not in n]
+        f.write("\n## One-time work before it (cold assembly + plan builds)\n\n")
+        table(f, lib + other)
     print("wrote launches")
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
