@@ -27,7 +27,8 @@ namespace skb {
 void count_launch(int n = 1);
 // profiling / test switches set by skb_debug_flags(): bit0 fused kernel skips P1,
 // bit1 skips P2, bit2 prints per-role cycle counts, bit3 forces the dense
-// (uncached) element-local kernel
+// (uncached) element-local kernel / the scalar hex kernel, bit5 P2 skips its
+// shared-memory gathers, bit6 P2 skips its global stores (bits 0,1,5,6: invalid results)
 int debug_flags();
 // SMs the persistent fused kernel leaves free (skb_sm_reserve): room for a
 // concurrent NCCL kernel when the interface exchange overlaps the next step
