@@ -141,7 +141,9 @@ int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *se
  * threads per CTA; records stream through a ring of `ring` (4|5) shared
  * buffers of rec_cap bytes by TMA bulk copies, vertex coordinates are gathered
  * with cp.async; vcap = most vertices in a tile.  (tile_elems, reduce_threads)
- * in {(256,128) (256,256) (512,128) (512,256) (512,384) (512,480) (768,224)};
+ * in {(128,96) (256,128) (256,224) (256,256) (384,224) (384,352) (512,128) (512,256)
+ * (512,384) (512,480) (768,224)}, one compute thread per element, or (512,736) (512,608)
+ * [256 compute threads, two elements each] (512,640) [128 compute threads, four each];
  * one more warp per CTA issues the TMA copies.
  * skb_p1_fused_smem_bytes gives the dynamic shared memory a configuration
  * needs (must be <= 227 KB).  tame != 0 asserts that every vertex coordinate is

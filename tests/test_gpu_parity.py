@@ -213,7 +213,9 @@ def test_quadrature_mismatch_errors():
 
 
 @pytest.mark.parametrize("tile,threads,ring", [(512, 256, 4), (512, 480, 5), (512, 128, 4),
-                                               (256, 128, 5), (256, 256, 4), (768, 224, 4)])
+                                               (256, 128, 5), (256, 256, 4), (768, 224, 4),
+                                               # 256 / 128 compute threads taking 2 / 4 elements each
+                                               (512, 736, 4), (512, 608, 5), (512, 640, 4)])
 def test_fused_p1_path(tile, threads, ring):
     """Warm re-assembly goes through the fused kernel (csrc/skb_p1_fused.cu):
     same plan (indptr/indices bit-exact), values within rtol 1e-12 of the
