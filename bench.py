@@ -155,7 +155,7 @@ def run_gpu(args):
     from skfem_b200 import form as _form
     _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads,
                       fused_ring=args.ring, fused_arith=args.arith,
-                      fused_spread=not args.no_spread)
+                      fused_spread=not args.no_spread, fused_l2_persist=args.l2_persist)
     cells = args.cells
     da = None
     if world == 1:
@@ -409,6 +409,8 @@ def main():
                          "the headline), fast = FMA + reciprocal (values within rtol 1e-12)")
     ap.add_argument("--no-spread", action="store_true", dest="no_spread",
                     help="keep the COO order inside the P2 lists (no plan-time bank spreading)")
+    ap.add_argument("--no-l2-persist", action="store_false", dest="l2_persist",
+                    help="do not pin the fused path's scratch array in L2 between its two kernels")
     ap.add_argument("--tile", type=int, default=512)
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--threads", type=int, default=480,

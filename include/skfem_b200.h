@@ -249,6 +249,11 @@ int skb_csr_spmv(const int32_t *indptr, const int32_t *indices, const double *da
 int skb_p1_plan_spread(uint16_t *rec16, const int64_t *grp_pos, const int32_t *grp_len,
                        int64_t ngroups, int32_t zero_base, void *stream);
 
+/* L2 residency window on `stream` (cudaStreamAttributeAccessPolicyWindow, persisting hits)
+ * for [ptr, ptr + bytes): used for the fused path's scratch array, written by the fused
+ * kernel and read by skb_p1_combine right after.  bytes == 0 resets the stream's policy. */
+int skb_l2_window(const void *ptr, int64_t bytes, void *stream);
+
 /* Tuning knob (process-wide, default 0): the persistent fused kernel sizes its
  * grid for (SM count - sms) SMs, leaving room for kernels of other streams - the
  * NCCL all-to-all of the multi-GPU path, which otherwise cannot start before the

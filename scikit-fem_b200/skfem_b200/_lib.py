@@ -52,6 +52,7 @@ SIGNATURES = {
     "skb_p1_fused_smem_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "skb_debug_flags": (None, [_INT]),
     "skb_sm_reserve": (None, [_INT]),
+    "skb_l2_window": (_INT, [_P, _I64, _P]),
     "skb_p1_combine": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "skb_p1_plan_spread": (_INT, [_P, _P, _P, _I64, _I32, _P]),
     "skb_facet_geometry": (_INT, [_SP, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I32,

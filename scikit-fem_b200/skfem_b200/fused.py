@@ -341,10 +341,14 @@ def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=Tr
     return None
 
 
-def run(fp, data, stream, fast=False):
+def run(fp, data, stream, fast=False, l2_persist=False):
     """Warm numeric phase: two kernel launches, nothing else.  ``fast``: fused
     multiply-add arithmetic in the element kernel (see csrc/skb_p1_fused.cu, FAST)."""
     lib = _lib.lib()
+    persist = l2_persist and fp.nscratch > 0
+    if persist:      # keep the tile partials in L2 between the two kernels
+        _lib.check(lib.skb_l2_window(fp.scratch.data_ptr(), 8 * fp.nscratch, stream),
+                   "skb_l2_window")
     code = lib.skb_p1tet_laplace_fused(
         fp.p.data_ptr(), fp.p.shape[1], fp.rec.data_ptr(), fp.rec_start.data_ptr(), fp.ntiles,
         fp.T, fp.threads, fp.ring, fp.rec_cap, fp.vcap, 2 if fast else fp.tame, C.c_double(fp.w),
@@ -354,6 +358,8 @@ def run(fp, data, stream, fast=False):
     code = lib.skb_p1_combine(fp.scratch.data_ptr(), fp.sptr.data_ptr(), fp.gslot.data_ptr(),
                               fp.gslot2.data_ptr(), fp.nshared, data.data_ptr(), stream)
     _lib.check(code, "skb_p1_combine")
+    if persist:
+        _lib.check(lib.skb_l2_window(None, 0, stream), "skb_l2_window")
 
 
 def stats(fp):
