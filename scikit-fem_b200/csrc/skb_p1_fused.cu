@@ -110,11 +110,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes,
-                                             uint64_t *bar) {
+// TMA bulk copy global -> shared, completion counted on an mbarrier; marked evict-first in L2:
+// the records are read once per step and must not push the vertex coordinates / tile partials
+// out of the L2 (measured: neutral on the step time, 0.1983 vs 0.1986 ms)
+__device__ __forceinline__ void tma_bulk_g2s_stream(void *dst, const void *src, unsigned bytes,
+                                                    uint64_t *bar) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
@@ -185,7 +191,7 @@ p1tet_laplace_fused_kernel(const P1Args a) {
     if (k < nk) {
       fence_proxy_async();
       mbar_expect_tx(&mbar[k % NR], nx_bytes);
-      tma_bulk_g2s(rec_of(k), a.rec + nx_b0, nx_bytes, &mbar[k % NR]);
+      tma_bulk_g2s_stream(rec_of(k), a.rec + nx_b0, nx_bytes, &mbar[k % NR]);
     }
   };
   auto wait_rec = [&](int k) { mbar_wait(&mbar[k % NR], (unsigned)((k / NR) & 1)); };
