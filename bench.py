@@ -304,10 +304,16 @@ def run_gpu(args):
         torch.cuda.synchronize()
         k_e2e = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
+        trace = []
         for _ in range(k_e2e):
+            t1 = time.perf_counter()
             Ah = e2e_step()
+            trace.append((1e3 * (time.perf_counter() - t1),
+                          torch.cuda.memory_allocated() >> 20, torch.cuda.memory_reserved() >> 20))
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / k_e2e
+        if os.environ.get("SKB_BENCH_TRACE"):
+            print("e2e per-iteration (ms, MiB allocated, MiB reserved):", trace, file=sys.stderr)
         if world > 1:
             tdt = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)

@@ -9,13 +9,24 @@ of ``p`` and ``t``.  The classes remain as the API objects a ``CellBasis`` is
 parameterised with; their array-returning methods evaluate on the device on
 demand (``skb_tabulate``) and copy back.
 """
+import weakref
+
 import numpy as np
 
 
 class Mapping:
     def __init__(self, mesh):
-        self.mesh = mesh
+        # weak: the mesh caches its mapping (Mesh._mapping); a strong back-reference would
+        # make every mesh (and the device copies of p and t it owns) wait for the cyclic GC
+        self._mesh = weakref.ref(mesh)
         self.dim = mesh.p.shape[0]
+
+    @property
+    def mesh(self):
+        m = self._mesh()
+        if m is None:
+            raise ReferenceError("the mesh of this mapping no longer exists")
+        return m
 
     def _basis(self, X, tind):
         from .basis import CellBasis

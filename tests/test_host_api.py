@@ -132,6 +132,26 @@ def test_get_dofs_facet_selectors_match_reference(name, M, E, args):
         basis.get_dofs('bottom')
 
 
+def test_mesh_and_basis_are_freed_without_the_cyclic_gc():
+    """A mesh owns the device copies of p and t: it (and a basis on it) must die by
+    reference counting, or re-assembly loops that build new meshes keep ~100 MB per
+    iteration alive until the cyclic GC runs (seen as e2e spikes in bench.py)."""
+    import gc
+    import weakref
+    gc.collect()
+    gc.disable()
+    try:
+        m = fem.MeshTet.init_tensor(*(3 * (np.linspace(0, 1, 4),)))
+        b = fem.Basis(m, fem.ElementTetP2())
+        fb = fem.FacetBasis(m, fem.ElementTetP2())
+        b.get_dofs(), m.f2t, b.mapping.mesh, fb.find
+        refs = [weakref.ref(o) for o in (m, b, fb)]
+        del m, b, fb
+        assert all(r() is None for r in refs)
+    finally:
+        gc.enable()
+
+
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "skfem_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)

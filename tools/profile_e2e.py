@@ -33,3 +33,24 @@ for rep in range(2):
     def full():
         mm = fem.MeshTet(p, t); bb = fem.Basis(mm, fem.ElementTetP1()); return laplace.assemble(bb)
     T("full e2e", full)
+
+# per-iteration wall time of the full cold call (detects allocator warm-up / bimodality)
+print("--- per-iteration full e2e (ms)")
+res = None
+ts = []
+for i in range(14):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = full()
+    torch.cuda.synchronize(); ts.append(1e3 * (time.perf_counter() - t0))
+print(" ".join("%.1f" % v for v in ts))
+# the same after a CUDA-graph capture (torch empties its allocator cache on capture)
+g = torch.cuda.CUDAGraph()
+bb2 = fem.Basis(m, fem.ElementTetP1()); laplace.assemble_device(bb2); out = torch.empty(laplace.assemble_device(bb2).nnz, dtype=torch.float64, device="cuda")
+with torch.cuda.graph(g):
+    laplace.assemble_device(bb2, out=out)
+ts = []
+for i in range(14):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = full()
+    torch.cuda.synchronize(); ts.append(1e3 * (time.perf_counter() - t0))
+print("after graph capture:", " ".join("%.1f" % v for v in ts))
