@@ -121,6 +121,10 @@ class InterfaceExchange:
         rowcount = torch.bincount(rows, minlength=self.nrows)[:self.nrows]
         self.indptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev),
                                  torch.cumsum(rowcount, 0)])
+        # the block is handed out like scipy's own CSR: int32 pattern whenever it fits
+        if self.nnz < 2 ** 31 and self.ncols < 2 ** 31:
+            self.indices = self.indices.to(torch.int32)
+            self.indptr = self.indptr.to(torch.int32)
         self.ro = np.concatenate([[0], np.cumsum(self.recv_counts)]).astype(np.int64)
         self.bytes_per_exchange = 8 * (sum(self.send_counts) - self.send_counts[rank])
         # ---- direct-write layout for the fused kernel --------------------------------
@@ -211,8 +215,11 @@ class DistributedCSR:
                 return h
             hd, hi, hp = d2h(self.data), d2h(self.indices), d2h(self.indptr)
             torch.cuda.current_stream().synchronize()
-            return csr_matrix((hd.numpy(), hi.numpy(), hp.numpy()), shape=(nrows, self.shape[1]),
-                              copy=False)
+            A = csr_matrix((hd.numpy(), hi.numpy(), hp.numpy()), shape=(nrows, self.shape[1]),
+                           copy=False)
+            A.has_sorted_indices = True      # sorted unique keys by construction
+            A.has_canonical_format = True
+            return A
         return csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
                            self.indptr.cpu().numpy()), shape=(nrows, self.shape[1]))
 
