@@ -24,7 +24,6 @@ import numpy as np
 
 from . import _lib
 from .dofs import Dofs
-from .element import Element, ElementVector
 from .quadrature import get_quadrature
 
 logger = logging.getLogger(__name__)

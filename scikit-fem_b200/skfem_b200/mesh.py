@@ -16,7 +16,6 @@ from __future__ import annotations
 import numpy as np
 
 from .element import ElementTriP1, ElementTetP1, ElementHex1
-from .refdom import RefTri, RefTet, RefHex
 
 
 def _cuda_ready():

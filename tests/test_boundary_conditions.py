@@ -85,7 +85,6 @@ def test_gpu_bc(name, M, E):
     Mref = Md.to_scipy()
     _, Me = fem.enforce(A, Md, D=D)
     Mexp = Mref.copy()
-    import scipy.sparse as sp
     rows = np.repeat(np.arange(Mref.shape[0]), np.diff(Mref.indptr))
     Mexp.data[np.isin(rows, D)] = 0.
     assert np.array_equal(Me.to_scipy().data, Mexp.data)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import skfem_b200 as fem
-from cases import CASES, LAME, load, mesh_of
+from cases import CASES, load, mesh_of
 from product import forms, mesh_from, element_from
 
 pytestmark = pytest.mark.gpu

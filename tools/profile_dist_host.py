@@ -10,8 +10,6 @@ import os
 import sys
 import time
 
-import numpy as np
-
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, os.path.join(ROOT, "scikit-fem_b200"))
 
