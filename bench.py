@@ -155,7 +155,8 @@ def run_gpu(args):
     from skfem_b200 import form as _form
     _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads,
                       fused_ring=args.ring, fused_arith=args.arith,
-                      fused_spread=not args.no_spread, fused_l2_persist=args.l2_persist)
+                      fused_spread=not args.no_spread, fused_l2_persist=args.l2_persist,
+                      fused_renumber=not args.no_renumber)
     cells = args.cells
     da = None
     if world == 1:
@@ -413,6 +414,8 @@ def main():
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"],
                     help="fused-kernel arithmetic: exact = reference operation order (default, "
                          "the headline), fast = FMA + reciprocal (values within rtol 1e-12)")
+    ap.add_argument("--no-renumber", action="store_true", dest="no_renumber",
+                    help="keep the tile-local vertex ids in global-id order (no bank colouring)")
     ap.add_argument("--no-spread", action="store_true", dest="no_spread",
                     help="keep the COO order inside the P2 lists (no plan-time bank spreading)")
     ap.add_argument("--no-l2-persist", action="store_false", dest="l2_persist",

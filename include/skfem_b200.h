@@ -249,6 +249,14 @@ int skb_csr_spmv(const int32_t *indptr, const int32_t *indices, const double *da
 int skb_p1_plan_spread(uint16_t *rec16, const int64_t *grp_pos, const int32_t *grp_len,
                        int64_t ngroups, int32_t zero_base, void *stream);
 
+/* Plan-time pass over the records' tl / verts sections: renumbers every tile's local vertex
+ * ids (bank pair + 16 * rank, greedy colouring of the (half-warp, slot) access sets) so that
+ * the fused kernel's coordinate gathers are free of shared-memory bank conflicts.  The
+ * vertex section of a record must hold 16 * (ceil(nv/16) + 1) entries (header word 0), all
+ * valid vertex ids.  In place; any consistent numbering is valid.                      */
+int skb_p1_plan_renumber(void *rec, const uint64_t *rec_start, int32_t ntiles,
+                         int32_t tile_elems, void *stream);
+
 /* L2 residency window on `stream` (cudaStreamAttributeAccessPolicyWindow, persisting hits)
  * for [ptr, ptr + bytes): used for the fused path's scratch array, written by the fused
  * kernel and read by skb_p1_combine right after.  bytes == 0 resets the stream's policy. */

@@ -155,3 +155,100 @@ extern "C" int skb_p1_plan_spread(uint16_t *rec16, const int64_t *grp_pos,
   count_launch();
   return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------
+// Tile-local vertex renumbering against the bank conflicts of P1's coordinate
+// gathers.  Thread e of a warp reads sx[tl[e].a] (a = 0..3): an LDS.64 served in
+// two half-warp passes, each as long as its most loaded bank pair (id mod 16).
+// Numbering the tile's vertices by ascending global id leaves 3.2 wavefronts per
+// gather on the 100^3 mesh (ncu 3.3); a greedy colouring - vertices taken in order
+// of first appearance, each getting the bank pair least used so far by the (half-
+// warp, slot) sets it belongs to, ids = colour + 16 * rank within the colour -
+// brings the model to 2.0, the minimum (tools/sim_smem_conflicts.py).
+// One thread per tile, in place on the record: rewrites tl and permutes verts;
+// unused ids (the vertex section is sized 16 * (ceil(nv/16) + 1) by the plan
+// builder) keep pointing at a valid vertex.
+// ---------------------------------------------------------------------------
+namespace skb {
+
+constexpr int RN_MAXV = 1024;   // vertices per tile handled (else the numbering is kept)
+constexpr int RN_MAXS = 16;     // (half-warp, slot) sets per vertex tracked
+
+__global__ void __launch_bounds__(32)
+p1_plan_renumber_kernel(unsigned char *__restrict__ rec, const uint64_t *__restrict__ rec_start,
+                        int ntiles, int T) {
+  const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= ntiles) return;
+  unsigned char *r = rec + rec_start[tile];
+  uint32_t *hdr = reinterpret_cast<uint32_t *>(r);
+  const int cap_ids = (int)hdr[0];                       // size of the vertex section
+  uint16_t *tl = reinterpret_cast<uint16_t *>(r + 32);   // [T][4]
+  int32_t *verts = reinterpret_cast<int32_t *>(r + hdr[2]);
+  const int nsets = (T / 16) * 4;
+  if (cap_ids > RN_MAXV || nsets > 255) return;
+  uint16_t newid[RN_MAXV];          // old id -> new id (0xFFFF = not seen yet)
+  uint16_t order[RN_MAXV];          // old ids in order of first appearance
+  unsigned char vset[RN_MAXV][RN_MAXS], vcnt[RN_MAXV];
+  unsigned char mask[256][16];      // per set: vertices per bank pair so far
+  int nv = 0, nseen = 0;
+  for (int i = 0; i < cap_ids; ++i) { newid[i] = 0xFFFF; vcnt[i] = 0; }
+  for (int s = 0; s < nsets; ++s)
+    for (int c = 0; c < 16; ++c) mask[s][c] = 0;
+  for (int e = 0; e < T; ++e) {
+    if (tl[e * 4] == 0xFFFF) continue;                   // padding element of the last tile
+    for (int a = 0; a < 4; ++a) {
+      const int v = tl[e * 4 + a];
+      if (v >= cap_ids) return;                          // malformed: keep everything
+      if (newid[v] == 0xFFFF) { newid[v] = 0xFFFE; order[nseen++] = (uint16_t)v; }
+      if (v + 1 > nv) nv = v + 1;
+      const unsigned char sid = (unsigned char)((e >> 4) * 4 + a);
+      bool have = false;
+      for (int k = 0; k < vcnt[v]; ++k) have |= vset[v][k] == sid;
+      if (!have && vcnt[v] < RN_MAXS) vset[v][vcnt[v]++] = sid;
+    }
+  }
+  if (nseen == 0) return;
+  const int per_colour = (nv + 15) / 16 + 1;             // ids < 16 * per_colour <= cap_ids
+  if (16 * per_colour > cap_ids) return;
+  int used[16];
+  for (int c = 0; c < 16; ++c) used[c] = 0;
+  for (int i = 0; i < nseen; ++i) {
+    const int v = order[i];
+    int best = -1, best_cost = 0x7fffffff;
+    for (int c = 0; c < 16; ++c) {
+      if (used[c] >= per_colour) continue;
+      int cost = 0;
+      for (int k = 0; k < vcnt[v]; ++k) cost += mask[vset[v][k]][c];
+      cost = cost * 1024 + used[c];
+      if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    newid[v] = (uint16_t)(best + 16 * used[best]);
+    ++used[best];
+    for (int k = 0; k < vcnt[v]; ++k) ++mask[vset[v][k]][best];
+  }
+  // permute the vertex list (through `order`/registers: no second buffer in the record)
+  int32_t keep = verts[order[0]];
+  // old global ids are needed after they are overwritten: stash them in local memory
+  int32_t oldv[RN_MAXV];
+  for (int i = 0; i < nv; ++i) oldv[i] = verts[i];
+  for (int i = 0; i < cap_ids; ++i) verts[i] = keep;     // holes point at a valid vertex
+  for (int i = 0; i < nseen; ++i) verts[newid[order[i]]] = oldv[order[i]];
+  for (int e = 0; e < T; ++e) {
+    if (tl[e * 4] == 0xFFFF) continue;
+    for (int a = 0; a < 4; ++a) tl[e * 4 + a] = newid[tl[e * 4 + a]];
+  }
+}
+
+}  // namespace skb
+
+extern "C" int skb_p1_plan_renumber(void *rec, const uint64_t *rec_start, int32_t ntiles,
+                                    int32_t tile_elems, void *stream) {
+  using namespace skb;
+  if (ntiles < 0 || tile_elems <= 0 || (tile_elems & 15)) return SKB_EINVAL;
+  if (ntiles == 0) return SKB_OK;
+  if (!rec || !rec_start) return SKB_EINVAL;
+  p1_plan_renumber_kernel<<<(ntiles + 31) / 32, 32, 0, (cudaStream_t)stream>>>(
+      (unsigned char *)rec, rec_start, ntiles, tile_elems);
+  count_launch();
+  return (int)cudaGetLastError();
+}

@@ -55,6 +55,7 @@ SIGNATURES = {
     "skb_l2_window": (_INT, [_P, _I64, _P]),
     "skb_p1_combine": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "skb_p1_plan_spread": (_INT, [_P, _P, _P, _I64, _I32, _P]),
+    "skb_p1_plan_renumber": (_INT, [_P, _P, _I32, _I32, _P]),
     "skb_facet_geometry": (_INT, [_SP, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I32,
                                   _P, _P, _P, _P, _P, _P]),
     "skb_facet_basis": (_INT, [_SP, _P, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P, _P]),

@@ -50,7 +50,7 @@ def _torch():
 # (fused multiply-adds + one reciprocal in the warm fused kernel: values within a few
 # ulp per term, i.e. inside the rtol 1e-12 bar, pattern unchanged)
 _CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring": 4,
-           "fused_arith": "exact", "fused_spread": True, "fused_l2_persist": True}
+           "fused_arith": "exact", "fused_spread": True, "fused_l2_persist": True, "fused_renumber": True}
 
 
 def set_options(**kw):
@@ -448,7 +448,8 @@ class BilinearForm(Form):
                     fp = fused.build_auto(ubasis, plan, T=fused_tile(),
                                           threads=int(_CONFIG["fused_threads"]),
                                           ring=int(_CONFIG["fused_ring"]), slot_map=slot_map,
-                                          spread=bool(_CONFIG["fused_spread"]))
+                                          spread=bool(_CONFIG["fused_spread"]),
+                                          renumber=bool(_CONFIG["fused_renumber"]))
                     ubasis._plans[fkey] = fp      # None: tiles too big, stay generic
                 if fp is not None:
                     data = out if out is not None else torch.empty(

@@ -75,7 +75,7 @@ def applicable(basis, form):
     return bool(np.all(W == W[0]))
 
 
-def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
+def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True, renumber=True):
     """``slot_map`` (optional int64 tensor, CSR slot -> output index): targets
     written by the kernels are remapped through it (multi-GPU direct write)."""
     torch = _torch()
@@ -119,7 +119,10 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
     uv_tile = uv // nv
     tile_vert_start = torch.searchsorted(uv_tile, tile_ids)
     nverts_tile = tile_vert_start[1:] - tile_vert_start[:-1]
-    fp.vcap = (int(nverts_tile.max()) + 1) // 2 * 2   # even: keeps shared sections 16 B aligned
+    # with renumbering (csrc/skb_p1_plan.cu) ids are bank pair + 16 * rank: the vertex
+    # section of a tile gets 16 * (ceil(nv / 16) + 1) entries, unused ones stay valid
+    nverts_sec = 16 * ((nverts_tile + 15) // 16 + 1) if renumber else nverts_tile
+    fp.vcap = (int(nverts_sec.max()) + 1) // 2 * 2    # even: keeps shared sections 16 B aligned
     if fp.vcap >= 0xFFFF:
         raise RuntimeError("fused plan: tile touches too many vertices")
     loc = (vinv - tile_vert_start[tile_of].repeat_interleave(4)).reshape(nel, 4)
@@ -240,7 +243,7 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
     # 6. pack the per-tile records
     HDR = 32
     off_verts = HDR + 8 * T
-    off_grp = off_verts + 4 * ((nverts_tile + 3) // 4 * 4)
+    off_grp = off_verts + 4 * ((nverts_sec + 3) // 4 * 4)
     off_meta = off_grp + 16 * ((ngroups_tile + 3) // 4)
     off_meta2 = off_meta + 128 * ngroups_tile
     off_fsel = off_meta2 + 128 * ngroups_tile        # one byte per lane: log2(F) of the leader
@@ -252,7 +255,7 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
     buf32 = torch.zeros(total // 4, dtype=torch.int32, device=dev)
     buf16 = buf32.view(torch.int16)
     rs = rec_start[:-1]
-    hdr = torch.stack([nverts_tile, ngroups_tile, torch.full_like(rs, off_verts), off_grp,
+    hdr = torch.stack([nverts_sec, ngroups_tile, torch.full_like(rs, off_verts), off_grp,
                        off_meta, off_ids, off_fsel, off_meta2], dim=1)
     buf32[(rs // 4)[:, None] + arange(8)[None, :]] = hdr.to(torch.int32)
     # tl (padding elements of the last tile: 0xFFFF)
@@ -263,6 +266,12 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
     buf16[((rs[tile_of] + HDR) // 2 + 4 * e_loc)[:, None] + arange(4)[None, :]] = \
         loc.to(torch.int16)
     # verts
+    if renumber:    # every id of the (larger) section points at a valid vertex of the tile
+        sec_tile = torch.repeat_interleave(arange(ntiles), nverts_sec)
+        sec_pos = arange(int(nverts_sec.sum())) - excl(nverts_sec)[sec_tile]
+        buf32[(rs[sec_tile] + off_verts) // 4 + sec_pos] = \
+            vert_gid[tile_vert_start[:-1]][sec_tile].to(torch.int32)
+        del sec_tile, sec_pos
     buf32[(rs[vert_tile] + off_verts) // 4 + vert_loc] = vert_gid.to(torch.int32)
     # grp: offset/32 | len << 16
     g_local = arange(ngroups) - tile_group_start[grp_tile]
@@ -304,6 +313,11 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
         torch.cuda.current_stream().synchronize()     # grp_pos / glen32 die here
     fp.rec = buf32
     fp.rec_start = rec_start.contiguous()            # int64 == uint64 for the kernel
+    if renumber and dev.type == "cuda":
+        code = _lib.lib().skb_p1_plan_renumber(
+            buf32.data_ptr(), fp.rec_start.data_ptr(), ntiles, T,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(code, "skb_p1_plan_renumber")
     fp.nts, fp.ncontrib, fp.ncontrib_sell, fp.ngroups = nts, ncontrib, ncontrib_sell, ngroups
     fp.nverts_tiles = int(vert_gid.shape[0])
     fp.rec_bytes = total
@@ -325,7 +339,8 @@ class FusedPlanTooBig(RuntimeError):
     pass
 
 
-def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True):
+def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True,
+               renumber=True):
     """Build with the requested tile, halving it while the tile's record ring
     and coordinates do not fit in shared memory (irregular meshes whose tiles
     touch many vertices).  Returns None if even the smallest tile is too big:
@@ -335,7 +350,7 @@ def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=Tr
     for tile, thr in options:
         try:
             return build(basis, plan, T=tile, threads=thr, ring=ring, slot_map=slot_map,
-                         spread=spread)
+                         spread=spread, renumber=renumber)
         except FusedPlanTooBig:
             continue
     return None
