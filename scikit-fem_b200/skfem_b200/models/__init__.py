@@ -1,2 +1,2 @@
 """Form library (the reference's ``skfem.models``)."""
-from . import poisson, elasticity  # noqa: F401
+from . import poisson, elasticity, general  # noqa: F401

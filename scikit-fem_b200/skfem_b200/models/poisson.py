@@ -1,37 +1,36 @@
-"""Poisson-type forms (skfem/models/poisson.py:7-24).
+"""Poisson-type library forms - the integrands of skfem/models/poisson.py:7-24.
 
-Each library form carries a ``native`` tag: ``Form.assemble`` recognises it and
-dispatches to the fused CUDA kernel for that integrand (geometry, push-forward
-and quadrature reduction in one pass) instead of tracing the Python callable.
-The callables remain valid definitions and are what the traced path executes
-when a fused kernel does not apply (e.g. two different bases).
+Every entry of the table below becomes a form object that carries a ``native`` tag
+``(kind, kernel id, parameters, field type)``: ``Form.assemble`` recognises the tag and
+launches the CUDA kernel written for that integrand (geometry, push-forward and
+quadrature reduction in one pass) instead of tracing the Python callable.  The callable
+stays a valid definition - it is what the traced path executes where no dedicated kernel
+applies (two different bases, a FacetBasis, extra parameters).
 """
+from .. import _lib
 from ..form import BilinearForm, LinearForm
-from ..helpers import grad, dot, ddot
-from .._lib import FORM_LAPLACE, FORM_MASS, FORM_VECTOR_LAPLACE, LFORM_UNIT_LOAD
+from ..helpers import ddot, dot, grad
 
 
-@BilinearForm
-def laplace(u, v, _):
-    return dot(grad(u), grad(v))
+def _library_form(wrapper, name, integrand, native):
+    integrand.__name__ = integrand.__qualname__ = name
+    form = wrapper(integrand)
+    form.native = native
+    return form
 
 
-@BilinearForm
-def vector_laplace(u, v, _):
-    return ddot(grad(u), grad(v))
+laplace = _library_form(
+    BilinearForm, "laplace", lambda u, v, w: dot(grad(u), grad(v)),
+    ("bilinear", _lib.FORM_LAPLACE, None, "scalar"))
 
+vector_laplace = _library_form(
+    BilinearForm, "vector_laplace", lambda u, v, w: ddot(grad(u), grad(v)),
+    ("bilinear", _lib.FORM_VECTOR_LAPLACE, None, "vector"))
 
-@BilinearForm
-def mass(u, v, _):
-    return u * v
+mass = _library_form(
+    BilinearForm, "mass", lambda u, v, w: u * v,
+    ("bilinear", _lib.FORM_MASS, None, "scalar"))
 
-
-@LinearForm
-def unit_load(v, _):
-    return v
-
-
-laplace.native = ("bilinear", FORM_LAPLACE, None, "scalar")
-vector_laplace.native = ("bilinear", FORM_VECTOR_LAPLACE, None, "vector")
-mass.native = ("bilinear", FORM_MASS, None, "scalar")
-unit_load.native = ("linear", LFORM_UNIT_LOAD, None, "scalar")
+unit_load = _library_form(
+    LinearForm, "unit_load", lambda v, w: v,
+    ("linear", _lib.LFORM_UNIT_LOAD, None, "scalar"))
