@@ -44,18 +44,28 @@ def _torch():
     return torch
 
 
-# fused_l2_persist: keep the fused path's per-tile partial sums (scratch) resident in L2
-# between the fused kernel and the combine kernel (-1.7 % on the warm step)
-# fused_arith: "exact" (reference operation order, bit-identical local data) or "fast"
-# (fused multiply-adds + one reciprocal in the warm fused kernel: values within a few
-# ulp per term, i.e. inside the rtol 1e-12 bar, pattern unchanged)
+# Engine options (set_options):
+#   fused             use the fused P1-tet Laplace path for warm re-assembly
+#   fused_tile        elements per tile (128 | 256 | 384 | 512 | 768, csrc/skb_p1_fused.cu)
+#   fused_threads     reduce threads per CTA (with fused_tile selects the kernel variant)
+#   fused_ring        record buffers in shared memory (4 | 5)
+#   fused_arith       "exact": reference operation order, bit-identical local data;
+#                     "fast": FMA + one reciprocal per element in the warm fused kernel
+#                     (values within a few ulp per term, inside the rtol 1e-12 bar; the
+#                     pattern is unaffected, it always comes from the exact cold pass)
+#   fused_spread      plan-time bank spreading of the P2 lists       (csrc/skb_p1_plan.cu)
+#   fused_renumber    plan-time conflict-free tile-local vertex ids  (csrc/skb_p1_plan.cu)
+#   fused_l2_persist  L2 persisting window on the per-tile partial sums between the fused
+#                     kernel and the combine kernel
 _CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring": 4,
-           "fused_arith": "exact", "fused_spread": True, "fused_l2_persist": True, "fused_renumber": True}
+           "fused_arith": "exact", "fused_spread": True, "fused_renumber": True,
+           "fused_l2_persist": True}
 
 
 def set_options(**kw):
-    """Engine switches: ``fused`` (use the fused P1 path for warm re-assembly),
-    ``fused_tile`` (elements per tile: 1024 or 2048)."""
+    """Set engine options (see the table above ``_CONFIG``); unknown names raise KeyError.
+    Options that shape the fused plan (tile, threads, ring, spread, renumber) apply to
+    plans built afterwards."""
     for k, v in kw.items():
         if k not in _CONFIG:
             raise KeyError(k)
