@@ -156,7 +156,7 @@ def run_gpu(args):
     _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads,
                       fused_ring=args.ring, fused_arith=args.arith,
                       fused_spread=not args.no_spread, fused_l2_persist=args.l2_persist,
-                      fused_renumber=not args.no_renumber)
+                      fused_renumber=not args.no_renumber, fused_tiling=args.tiling)
     cells = args.cells
     da = None
     if world == 1:
@@ -420,6 +420,9 @@ def main():
                     help="keep the COO order inside the P2 lists (no plan-time bank spreading)")
     ap.add_argument("--no-l2-persist", action="store_false", dest="l2_persist",
                     help="do not pin the fused path's scratch array in L2 between its two kernels")
+    ap.add_argument("--tiling", default="morton", choices=["morton", "kd"],
+                    help="fused plan: how elements are cut into tiles (kd = compact k-d boxes, "
+                         "opt-in until timed)")
     ap.add_argument("--tile", type=int, default=512)
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--threads", type=int, default=480,

@@ -57,9 +57,13 @@ def _torch():
 #   fused_renumber    plan-time conflict-free tile-local vertex ids  (csrc/skb_p1_plan.cu)
 #   fused_l2_persist  L2 persisting window on the per-tile partial sums between the fused
 #                     kernel and the combine kernel
+#   fused_tiling      "morton": tiles = a Morton curve over the element centroids cut every
+#                     fused_tile elements; "kd": compact boxes from a balanced k-d tree
+#                     (fused._kd_order; fewer CSR slots shared between tiles - plan-only
+#                     change, not yet timed on a B200, hence opt-in)
 _CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring": 4,
            "fused_arith": "exact", "fused_spread": True, "fused_renumber": True,
-           "fused_l2_persist": True}
+           "fused_l2_persist": True, "fused_tiling": "morton"}
 
 
 def set_options(**kw):
@@ -459,7 +463,8 @@ class BilinearForm(Form):
                                           threads=int(_CONFIG["fused_threads"]),
                                           ring=int(_CONFIG["fused_ring"]), slot_map=slot_map,
                                           spread=bool(_CONFIG["fused_spread"]),
-                                          renumber=bool(_CONFIG["fused_renumber"]))
+                                          renumber=bool(_CONFIG["fused_renumber"]),
+                                          tiling=str(_CONFIG["fused_tiling"]))
                     ubasis._plans[fkey] = fp      # None: tiles too big, stay generic
                 if fp is not None:
                     data = out if out is not None else torch.empty(

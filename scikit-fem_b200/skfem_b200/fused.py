@@ -59,6 +59,55 @@ def _spread10(v):
     return v
 
 
+def _kd_order(corner, T):
+    """Element order whose consecutive chunks of T are compact boxes: a balanced k-d tree
+    over the elements' bounding-box corners, every split placed after a whole number of tiles
+    (left child = floor(k/2) full tiles), sorted along the segment's longest axis with the
+    other two axes as tie-breakers.  All levels are processed at once with segmented sorts
+    (two stable argsorts per level, ~log2(ntiles) levels).  Compared with cutting a Morton
+    curve every T elements this leaves fewer CSR slots shared between tiles (C2: 49 % instead
+    of 65 % of the canonical slots, 29 % fewer per-tile partials; tools/store_sectors.py)."""
+    torch = _torch()
+    dev = corner.device
+    i64 = torch.int64
+    nel = int(corner.shape[1])
+    lo = corner.min(dim=1, keepdim=True).values
+    hi = corner.max(dim=1, keepdim=True).values
+    scale = float(2 ** 20 - 1)
+    q = ((corner - lo) / torch.clamp(hi - lo, min=1e-300) * scale).clamp(0, scale).to(i64)
+    order = torch.arange(nel, device=dev, dtype=i64)
+    pos = torch.arange(nel, device=dev, dtype=i64)
+    seg_cnt = torch.tensor([nel], device=dev, dtype=i64)
+    seg_k = torch.tensor([(nel + T - 1) // T], device=dev, dtype=i64)
+    while int(seg_k.max()) > 1:
+        nseg = int(seg_cnt.shape[0])
+        seg_of = torch.repeat_interleave(torch.arange(nseg, device=dev, dtype=i64), seg_cnt)
+        qq = q[:, order]
+        idx3 = seg_of.expand(3, -1)
+        mn = torch.full((3, nseg), 2 ** 20, device=dev, dtype=i64).scatter_reduce_(
+            1, idx3, qq, reduce="amin", include_self=True)
+        mx = torch.full((3, nseg), -1, device=dev, dtype=i64).scatter_reduce_(
+            1, idx3, qq, reduce="amax", include_self=True)
+        axs = torch.argsort(mn - mx, dim=0, stable=True)        # longest extent first
+        k0 = torch.gather(qq, 0, axs[0][seg_of][None])[0]
+        k1 = torch.gather(qq, 0, axs[1][seg_of][None])[0]
+        k2 = torch.gather(qq, 0, axs[2][seg_of][None])[0]
+        key = (k0 << 42) | (k1 << 21) | k2
+        key = torch.where((seg_k == 1)[seg_of], pos, key)        # finished tiles keep their order
+        p1 = torch.argsort(key, stable=True)
+        perm = p1[torch.argsort(seg_of[p1], stable=True)]
+        order = order[perm]
+        split = seg_k > 1
+        kl = torch.where(split, seg_k // 2, seg_k)
+        kr = seg_k - kl
+        cl = torch.where(split, kl * T, seg_cnt)
+        cnt2 = torch.stack([cl, seg_cnt - cl], dim=1).reshape(-1)
+        k2n = torch.stack([kl, kr], dim=1).reshape(-1)
+        keep = k2n > 0
+        seg_cnt, seg_k = cnt2[keep], k2n[keep]
+    return order
+
+
 class P1FusedPlan:
     pass
 
@@ -75,9 +124,14 @@ def applicable(basis, form):
     return bool(np.all(W == W[0]))
 
 
-def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True, renumber=True):
+def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True, renumber=True,
+          tiling="morton"):
     """``slot_map`` (optional int64 tensor, CSR slot -> output index): targets
-    written by the kernels are remapped through it (multi-GPU direct write)."""
+    written by the kernels are remapped through it (multi-GPU direct write).
+    ``tiling``: "morton" cuts a Morton curve over the element centroids every T elements;
+    "kd" builds compact boxes with a balanced k-d tree (``_kd_order``)."""
+    if tiling not in ("morton", "kd"):
+        raise ValueError("fused plan: unknown tiling '{}'".format(tiling))
     torch = _torch()
     d = basis._dev()
     dev = d["device"]
@@ -88,6 +142,7 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True, r
     N = int(plan.shape[1])
     fp = P1FusedPlan()
     fp.T, fp.threads, fp.ring, fp.nel, fp.nnz = T, threads, ring, nel, nnz
+    fp.tiling = tiling
     ntiles = (nel + T - 1) // T
     fp.ntiles = ntiles
     i64 = torch.int64
@@ -99,14 +154,17 @@ def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True, r
         return torch.cumsum(x, 0) - x
 
     tl = t.long()
-    # 1. Morton order of element centroids
-    cent = p[:, tl].sum(dim=1)                      # (3, nel), 4x centroid
-    lo = cent.min(dim=1, keepdim=True).values
-    hi = cent.max(dim=1, keepdim=True).values
-    q = ((cent - lo) / torch.clamp(hi - lo, min=1e-300) * 1023.0).clamp(0, 1023).to(i64)
-    code = _spread10(q[0]) | (_spread10(q[1]) << 1) | (_spread10(q[2]) << 2)
-    order = torch.argsort(code, stable=True)
-    del cent, q, code
+    # 1. element order: consecutive chunks of T elements are the tiles
+    if tiling == "kd":
+        order = _kd_order(p[:, tl].min(dim=1).values, T)
+    else:                                           # Morton order of element centroids
+        cent = p[:, tl].sum(dim=1)                  # (3, nel), 4x centroid
+        lo = cent.min(dim=1, keepdim=True).values
+        hi = cent.max(dim=1, keepdim=True).values
+        q = ((cent - lo) / torch.clamp(hi - lo, min=1e-300) * 1023.0).clamp(0, 1023).to(i64)
+        code = _spread10(q[0]) | (_spread10(q[1]) << 1) | (_spread10(q[2]) << 2)
+        order = torch.argsort(code, stable=True)
+        del cent, q, code
     tt = tl[:, order].t().contiguous()              # (nel, 4) int64, tile order
     e_idx = arange(nel)
     tile_of = e_idx // T
@@ -340,7 +398,7 @@ class FusedPlanTooBig(RuntimeError):
 
 
 def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True,
-               renumber=True):
+               renumber=True, tiling="morton"):
     """Build with the requested tile, halving it while the tile's record ring
     and coordinates do not fit in shared memory (irregular meshes whose tiles
     touch many vertices).  Returns None if even the smallest tile is too big:
@@ -350,7 +408,7 @@ def build_auto(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=Tr
     for tile, thr in options:
         try:
             return build(basis, plan, T=tile, threads=thr, ring=ring, slot_map=slot_map,
-                         spread=spread, renumber=renumber)
+                         spread=spread, renumber=renumber, tiling=tiling)
         except FusedPlanTooBig:
             continue
     return None
@@ -389,4 +447,5 @@ def stats(fp):
     b["tile_slots_per_csr_slot"] = fp.nts / max(fp.nnz, 1)
     b["vcap"], b["rec_cap"], b["smem"] = fp.vcap, fp.rec_cap, fp.smem
     b["sell_padding"] = fp.ncontrib_sell / max(fp.ncontrib, 1)
+    b["shared_slots"], b["tiling"] = fp.nshared, getattr(fp, "tiling", "morton")
     return b

@@ -115,8 +115,10 @@ def _emulate(fp, p, T):
     return csr
 
 
-@pytest.mark.parametrize("T,morph", [(128, False), (256, True), (512, True)])
-def test_fused_plan_records_reproduce_the_csr(T, morph):
+@pytest.mark.parametrize("T,morph,tiling", [(128, False, "morton"), (256, True, "morton"),
+                                            (512, True, "morton"), (128, False, "kd"),
+                                            (256, True, "kd"), (512, True, "kd")])
+def test_fused_plan_records_reproduce_the_csr(T, morph, tiling):
     import os
     from oracle import skfem_oracle as O
     from skfem_b200 import _lib, fused
@@ -130,7 +132,7 @@ def test_fused_plan_records_reproduce_the_csr(T, morph):
         q[1] = m.p[1] + 0.02 * m.p[2] ** 2
         m = mesh_of(dict(p=q, t=m.t), "tet")
     basis, plan, A = _plan_on_cpu(m)
-    fp = fused.build(basis, plan, T=T)
+    fp = fused.build(basis, plan, T=T, tiling=tiling)
     assert fp.ntiles == -(-m.t.shape[1] // T) and fp.rec_cap % 16 == 0
     assert (fp.rec_start.numpy() % 16 == 0).all()
     csr = _emulate(fp, m.p, T)
@@ -138,3 +140,25 @@ def test_fused_plan_records_reproduce_the_csr(T, morph):
     np.testing.assert_allclose(csr, A.data, rtol=1e-11, atol=1e-12 * np.abs(A.data).max())
     st = fused.stats(fp)
     assert st["sell_padding"] >= 1.0 and st["tile_slots_per_csr_slot"] >= 0.5
+
+
+def test_kd_tiling_is_a_permutation_and_shares_fewer_slots():
+    """fused._kd_order: every element exactly once, tiles = consecutive chunks of T, and on a
+    Kuhn grid fewer canonical CSR slots are shared between tiles than with the Morton cut."""
+    import os
+    from oracle import skfem_oracle as O
+    from skfem_b200 import _lib, fused
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    g1 = np.linspace(0, 1, 13)
+    m = O.mesh_tet_tensor(g1, g1, g1)
+    corner = torch.from_numpy(m.p[:, m.t].min(axis=1))
+    for T in (128, 512, 500):
+        order = fused._kd_order(corner, T).numpy()
+        assert np.array_equal(np.sort(order), np.arange(m.t.shape[1]))
+    basis, plan, _ = _plan_on_cpu(m)
+    shared = {tl: fused.build(basis, plan, T=512, tiling=tl).nshared for tl in ("morton", "kd")}
+    assert shared["kd"] < shared["morton"]
+    with pytest.raises(ValueError):
+        fused.build(basis, plan, T=512, tiling="hilbert")

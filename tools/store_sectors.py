@@ -3,7 +3,7 @@
 Builds the fused-path plan on CPU tensors (the builder is torch-only), decodes meta / meta2 of
 every 32-lane group and counts the distinct 32-byte sectors each of the kernel's three store
 instructions (csr_data[m], scratch[m & ~bit31], csr_data[m2]) touches.  The lower bound is
-ceil(active lanes / 4).  Usage: python tools/store_sectors.py [cells_per_side] [--morph]
+ceil(active lanes / 4).  Usage: python tools/store_sectors.py [cells_per_side] [--morph] [--kd]
 """
 import os
 import sys
@@ -68,10 +68,13 @@ def main():
         q[0] = m.p[0] + 0.03 * np.sin(7 * m.p[1])
         q[1] = m.p[1] + 0.02 * m.p[2] ** 2
         m = SimpleNamespace(p=np.ascontiguousarray(q), t=np.ascontiguousarray(m.t), refdom="tet")
-    fp = plan_on_cpu(m, 512)
+    fp = plan_on_cpu(m, 512, tiling="kd" if "--kd" in sys.argv else "morton")
     st = fused.stats(fp)
     tot = sectors(fp)
-    print("tiles %d, ELL padding %.3f" % (fp.ntiles, st["sell_padding"]))
+    print("tiling %s: tiles %d, ELL padding %.3f, record bytes per tile %.0f, vcap %d, smem %d, "
+          "tile slots %d, bytes per element %.1f"
+          % (st["tiling"], fp.ntiles, st["sell_padding"], st["records"] / fp.ntiles, st["vcap"],
+             st["smem"], fp.nts, st["per_element"]))
     ncanon = (fp.nnz + int(m.p.shape[1])) // 2          # canonical slots: row <= col
     print("canonical CSR slots %d, shared between tiles %d (%.1f %%), partials %d"
           % (ncanon, fp.nshared, 100.0 * fp.nshared / ncanon, fp.nscratch))
