@@ -5,6 +5,8 @@ Bar (BASELINE.json north_star): DOF numbering, indptr and indices bit-exact;
 element-local data bit-exact (array_equal) wherever the arithmetic contract
 allows it; CSR values within rtol 1e-12 (+ atol 1e-12*max|A| for noise-level
 entries); load vectors bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -366,3 +368,36 @@ def test_fused_fast_arithmetic_within_tolerance():
     np.testing.assert_allclose(A1.data, ref.data, rtol=1e-12, atol=1e-12 * scale)
     np.testing.assert_allclose(A3.data, ref.data, rtol=1e-12, atol=1e-12 * scale)
     print("fast vs exact max rel diff", np.abs(A1.data - A3.data).max() / scale)
+
+
+@pytest.mark.skipif(os.environ.get("SKB_TEST_EXPERIMENTAL") != "1",
+                    reason="opt-in engine options not yet timed / verified on a B200 "
+                           "(set SKB_TEST_EXPERIMENTAL=1)")
+def test_fused_kd_tiling_parity():
+    """Opt-in k-d tiling of the fused plan (fused._kd_order): same CSR as the oracle on a
+    Kuhn grid (value-dependent 7-point pattern) and on a morphed, non-uniform one."""
+    from oracle import skfem_oracle as O
+    from skfem_b200.form import set_options
+    from skfem_b200.models.poisson import laplace
+    g = np.linspace(0, 1, 17)
+    cases = [fem.MeshTet.init_tensor(g, g, g)]
+    q = cases[0].p.copy()
+    q[0] = q[0] + 0.03 * np.sin(7 * q[1])
+    q[1] = q[1] + 0.02 * q[2] ** 2
+    cases.append(fem.MeshTet(q, cases[0].t))
+    try:
+        set_options(fused_tiling="kd")
+        for m in cases:
+            om = mesh_of(dict(p=m.p, t=m.t), "tet")
+            ref = O.assemble_bilinear(O.laplace, O.cell_basis(om, O.element("tet_p1")))
+            b = fem.Basis(m, fem.ElementTetP1())
+            laplace.assemble(b)                   # cold: generic path builds the pattern
+            A1 = laplace.assemble(b)              # warm: fused kernel on the k-d plan
+            A2 = laplace.assemble(b)
+            assert np.array_equal(A1.indptr, ref.indptr)
+            assert np.array_equal(A1.indices, ref.indices)
+            assert np.array_equal(A1.data, A2.data)
+            scale = np.abs(ref.data).max()
+            np.testing.assert_allclose(A1.data, ref.data, rtol=1e-12, atol=1e-12 * scale)
+    finally:
+        set_options(fused_tiling="morton")
