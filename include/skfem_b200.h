@@ -68,7 +68,7 @@ typedef struct skb_space {
   const double *W;    /* (nqp,)            quadrature weights               */
   const double *mdphi;/* (nnodes, dim, nqp) mapping-element gradients, ISO only */
   const double *mphi; /* (nnodes, nqp)      mapping-element values, ISO only (global coords) */
-  const double *X;    /* (dim, nqp) quadrature points, needed by skb_global_coords (affine) */
+  const double *X;    /* (dim, nqp) quadrature points, needed by skb_tabulate's x output (affine) */
 } skb_space_t;
 
 /* ---- element-local data: replaces CellBasis.__init__ + Form._assemble ----
