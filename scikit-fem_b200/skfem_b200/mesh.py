@@ -420,6 +420,39 @@ class MeshTet(Mesh):
                 [0, 3, 5, 7], [0, 2, 6, 7], [0, 3, 6, 7])
         return cls(p, np.hstack([c[rows] for rows in kuhn]))
 
+    # local edges (rows of t2e) that meet at local vertex 0..3
+    _CORNER_EDGES = ((0, 2, 3), (0, 1, 4), (1, 2, 5), (3, 4, 5))
+    # the inner octahedron has three diagonals, each joining the midpoints of two opposite
+    # edges; cut along diagonal (a, b) it falls into four tets (a, b, x, y) with (x, y) from
+    # the ring of the remaining four midpoints
+    _OCTA = (((2, 4), ((0, 1), (0, 3), (1, 5), (3, 5))),
+             ((1, 3), ((0, 4), (4, 5), (5, 2), (2, 0))),
+             ((0, 5), ((1, 4), (4, 3), (3, 2), (2, 1))))
+
+    def _uniform(self):
+        """Regular 1:8 refinement (the scheme of mesh_tet_1.py:84-126): vertices at the edge
+        midpoints, one child per corner, the inner octahedron cut along its shortest diagonal
+        - measured, like the reference, in the x-y plane only; ties go to the later diagonal.
+        Children are ordered corner-major, then ring-position-major / diagonal-minor."""
+        p, t = self.p, self.t
+        mid = self.t2e + p.shape[1]                       # vertex id of every local edge midpoint
+        newp = np.hstack((p, p[:, self.edges].mean(axis=1)))
+
+        def d2(a, b):                                     # squared x-y distance of two midpoints
+            return ((newp[0, mid[a]] - newp[0, mid[b]]) ** 2
+                    + (newp[1, mid[a]] - newp[1, mid[b]]) ** 2)
+        d = [d2(a, b) for (a, b), _ in self._OCTA]
+        pick = (np.logical_and(d[0] < d[1], d[0] < d[2]),
+                np.logical_and(~(d[0] < d[1]), d[1] < d[2]),
+                np.logical_and(~(d[0] < d[2]), ~(d[1] < d[2])))
+        children = [np.vstack((t[v],) + tuple(mid[e] for e in self._CORNER_EDGES[v]))
+                    for v in range(4)]
+        for ring in range(4):
+            for ((a, b), pairs), sel in zip(self._OCTA, pick):
+                x, y = pairs[ring]
+                children.append(np.vstack((mid[a, sel], mid[b, sel], mid[x, sel], mid[y, sel])))
+        return type(self)(newp, np.hstack(children))
+
 
 class MeshHex(Mesh):
     elem = ElementHex1
@@ -436,6 +469,35 @@ class MeshHex(Mesh):
     def init_tensor(cls, x, y, z):
         p, c, _ = _tensor_grid(x, y, z)
         return cls(p, c)
+
+    def _uniform(self):
+        """1:8 refinement (the scheme of mesh_hex_1.py:57-95): new nodes at the edge midpoints,
+        facet centres and cell centres, numbered in that order after the old vertices.  Child
+        k keeps the parent's local orientation: its local node j is the centre of the smallest
+        sub-entity of the parent (vertex, edge, facet, cell) that contains the parent's local
+        vertices k and j - derived here from RefHex instead of a written-out table."""
+        p, t, rd = self.p, self.t, self.refdom
+        edge_node = self.t2e + p.shape[1]
+        facet_node = self.t2f + p.shape[1] + self.edges.shape[1]
+        cell_node = (np.arange(t.shape[1], dtype=np.int64)
+                     + p.shape[1] + self.edges.shape[1] + self.facets.shape[1])
+        newp = np.hstack((p,
+                          .5 * np.sum(p[:, self.edges], axis=1),
+                          .25 * np.sum(p[:, self.facets], axis=1),
+                          .125 * np.sum(p[:, t], axis=1)))
+
+        def centre(k, j):
+            if k == j:
+                return t[k]
+            for i, e in enumerate(rd.edges):
+                if {k, j} == set(e):
+                    return edge_node[i]
+            for i, f in enumerate(rd.facets):
+                if {k, j} <= set(f):
+                    return facet_node[i]
+            return cell_node
+        newt = np.hstack([np.vstack([centre(k, j) for j in range(8)]) for k in range(8)])
+        return type(self)(newp, newt)
 
 
 MeshTri1, MeshTet1, MeshHex1 = MeshTri, MeshTet, MeshHex

@@ -46,6 +46,10 @@ def test_mesh_constructors_match_reference():
     g = load("hex1_tensor3")
     m = fem.MeshHex.init_tensor(*(3 * (np.linspace(0, 1, 4),)))
     assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
+    g = load("tet_p1_refined3")                 # MeshTet().refined(3), SURVEY 8d parity extra
+    m = fem.MeshTet().refined(3)
+    assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
+    assert m.t.dtype == np.int32
     g = load("tri_p1_two_triangles")
     m = fem.MeshTri()
     assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
@@ -180,3 +184,26 @@ def test_no_cpu_fallback_without_gpu():
     b = fem.Basis(fem.MeshTri(), fem.ElementTriP1())
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         laplace.assemble(b)
+
+
+def test_uniform_refinement_of_tets_and_hexes_matches_reference():
+    """MeshTet / MeshHex .refined against fixtures written by the real reference
+    (tools/gen_golden_mesh.py): same vertices, same children, same order, int32."""
+    g = load("mesh_refined")
+    x, y, z = g["x"], g["y"], g["z"]
+    cases = {
+        "tet_default_r2": fem.MeshTet().refined(2),
+        "tet_tensor_r1": fem.MeshTet.init_tensor(x, y, z).refined(),
+        "hex_default_r2": fem.MeshHex().refined(2),
+        "hex_tensor_r1": fem.MeshHex.init_tensor(x, y, z).refined(1),
+    }
+    for name, m in cases.items():
+        assert np.array_equal(m.p, g[name + "_p"]), name
+        assert np.array_equal(m.t, g[name + "_t"]) and m.t.dtype == np.int32, name
+    # a refined mesh is a full citizen: entities and a quadratic basis can be built on it
+    m = cases["hex_tensor_r1"]
+    assert m.facets.shape[0] == 4 and m.t2e.shape == (12, m.t.shape[1])
+    b = fem.Basis(cases["tet_tensor_r1"], fem.ElementTetP2())
+    assert b.N == cases["tet_tensor_r1"].p.shape[1] + cases["tet_tensor_r1"].edges.shape[1]
+    with pytest.raises(NotImplementedError):
+        type("M", (fem.mesh.Mesh,), {})._uniform(m)

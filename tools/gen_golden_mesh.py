@@ -1,0 +1,35 @@
+"""Golden vectors for the mesh constructors that have no other fixture: uniform refinement of
+tetrahedral and hexahedral meshes (mesh_tet_1.py:84-126, mesh_hex_1.py:57-95), produced by the
+real reference.  Run in the build container only:
+
+    PYTHONPATH=/root/reference python tools/gen_golden_mesh.py
+"""
+import os
+
+import numpy as np
+import skfem
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                   "tests", "golden", "mesh_refined.npz")
+
+
+def main():
+    x = np.array([0., 0.2, 0.55, 1.])
+    y = np.array([0., 0.4, 1.])
+    z = np.array([0., 0.1, 0.35, 0.8, 1.])
+    out = {"x": x, "y": y, "z": z}
+    cases = {
+        "tet_default_r2": skfem.MeshTet().refined(2),
+        "tet_tensor_r1": skfem.MeshTet.init_tensor(x, y, z).refined(1),
+        "hex_default_r2": skfem.MeshHex().refined(2),
+        "hex_tensor_r1": skfem.MeshHex.init_tensor(x, y, z).refined(1),
+    }
+    for name, m in cases.items():
+        out[name + "_p"] = m.p
+        out[name + "_t"] = m.t
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
