@@ -257,6 +257,7 @@ class Mesh:
             named[name] = (self.facets_satisfying(spec, boundaries_only=boundaries_only)
                            if callable(spec) else np.asarray(spec, dtype=np.int32))
         out.boundaries = named
+        out.subdomains = self.subdomains
         for attr in ("_facets", "_t2f", "_edges", "_t2e", "_f2t", "_nvertices"):
             if hasattr(self, attr):
                 setattr(out, attr, getattr(self, attr))
@@ -282,12 +283,62 @@ class Mesh:
         raise NotImplementedError
 
     def normalize_elements(self, elements):
+        """Element indices from an index, an index / boolean array, a test on element
+        midpoints, a subdomain name, or a list / set of those (mesh.py:1331-1368)."""
+        if isinstance(elements, bool):
+            if elements:
+                return np.arange(self.nelements, dtype=np.int32)
+            raise NotImplementedError
         if isinstance(elements, (int, np.integer)):
             return np.array([elements], dtype=np.int32)
+        if callable(elements):
+            return self.elements_satisfying(elements)
+        if isinstance(elements, str):
+            if self.subdomains is not None and elements in self.subdomains:
+                return self.subdomains[elements]
+            raise ValueError("Subdomain '{}' not found.".format(elements))
+        if isinstance(elements, (tuple, list, set)):
+            if len(elements) == 0:
+                return np.zeros(0, dtype=np.int32)
+            return np.unique(np.concatenate([self.normalize_elements(e) for e in elements]))
         arr = np.asarray(elements)
         if arr.dtype == bool:
             arr = np.nonzero(arr)[0]
         return arr.astype(np.int32)
+
+    # -- selections on nodes / elements (mesh.py:402-424,476-493,251-275) ---------
+    subdomains = None  # optional {name: element indices}
+
+    def interior_nodes(self):
+        return np.setdiff1d(np.arange(self.p.shape[1]), self.boundary_nodes())
+
+    def nodes_satisfying(self, test, boundaries_only=False):
+        nodes = np.nonzero(test(self.p))[0].astype(np.int32)
+        return np.intersect1d(nodes, self.boundary_nodes()) if boundaries_only else nodes
+
+    def elements_satisfying(self, test):
+        """Elements whose midpoint (mean of the vertices) satisfies ``test``."""
+        return np.nonzero(test(self.p[:, self.t].mean(axis=1)))[0].astype(np.int32)
+
+    def with_subdomains(self, subdomains):
+        """Copy of the mesh with named element sets ``{name: indices | test on midpoints}``."""
+        out = self.with_boundaries({})
+        out.boundaries = self.boundaries
+        named = dict(self.subdomains or {})
+        for name, spec in subdomains.items():
+            named[name] = self.elements_satisfying(spec) if callable(spec) else spec
+        out.subdomains = named
+        return out
+
+    def params(self):
+        """Per element, the length of its longest edge (mesh_2d.py:12-17, mesh_3d.py:13-17)."""
+        ents, t2x = (self.edges, self.t2e) if self.dim() == 3 else (self.facets, self.t2f)
+        length = np.linalg.norm(np.diff(self.p[:, ents], axis=1), axis=0)[0]
+        return length[t2x].max(axis=0)
+
+    def param(self):
+        """Mesh parameter h: the longest edge of the mesh."""
+        return np.max(self.params())
 
     # -- geometry --------------------------------------------------------------
     def _mapping(self):
@@ -419,6 +470,23 @@ class MeshTet(Mesh):
         kuhn = ([0, 1, 5, 7], [0, 1, 4, 7], [0, 2, 4, 7],
                 [0, 3, 5, 7], [0, 2, 6, 7], [0, 3, 6, 7])
         return cls(p, np.hstack([c[rows] for rows in kuhn]))
+
+    @classmethod
+    def init_ball(cls, nrefs=3):
+        """Unit ball (mesh_tet_1.py:396-428): the octahedron with vertices 0, +e_i (1..3),
+        -e_i (4..6) cut into one tet per octant, refined ``nrefs`` times; after every
+        refinement the boundary nodes are pushed out onto the unit sphere."""
+        p = np.vstack((np.zeros((1, 3)), np.eye(3), 0. - np.eye(3))).T   # 0. - x: no -0.0
+        octants = [[0, 1, 2, 3], [0, 4, 5, 6], [0, 1, 2, 6], [0, 1, 3, 5],
+                   [0, 2, 3, 4], [0, 4, 5, 3], [0, 4, 6, 2], [0, 5, 6, 1]]
+        m = cls(p, np.array(octants, dtype=np.int32).T)
+        for _ in range(nrefs):
+            m = m.refined()
+            q = m.p.copy()
+            shell = m.boundary_nodes()
+            q[:, shell] = q[:, shell] / np.linalg.norm(q[:, shell], axis=0)
+            m = cls(q, m.t)
+        return m
 
     # local edges (rows of t2e) that meet at local vertex 0..3
     _CORNER_EDGES = ((0, 2, 3), (0, 1, 4), (1, 2, 5), (3, 4, 5))

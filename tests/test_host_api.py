@@ -207,3 +207,39 @@ def test_uniform_refinement_of_tets_and_hexes_matches_reference():
     assert b.N == cases["tet_tensor_r1"].p.shape[1] + cases["tet_tensor_r1"].edges.shape[1]
     with pytest.raises(NotImplementedError):
         type("M", (fem.mesh.Mesh,), {})._uniform(m)
+
+
+def test_mesh_selections_parameters_and_ball_match_reference():
+    """init_ball, params, node / element selections, named subdomains and Basis(elements=name)
+    against fixtures from the real reference (tools/gen_golden_mesh.py, tools/gen_golden.py)."""
+    g = load("tet_p1_ball2")
+    m = fem.MeshTet.init_ball(2)
+    assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
+    p0 = fem.MeshTet.init_ball(0).p                   # the octahedron: no negative zeros
+    assert not np.signbit(p0[p0 == 0]).any()
+    g = load("mesh_refined")
+    x, y, z = g["x"], g["y"], g["z"]
+    low = lambda q: q[0] < 0.5                                   # noqa: E731
+    meshes = {"tet": (fem.MeshTet.init_tensor(x, y, z), fem.ElementTetP2),
+              "tri": (fem.MeshTri().refined(3), fem.ElementTriP2),
+              "hex": (fem.MeshHex.init_tensor(x, y, z), fem.ElementHex2)}
+    for name, (m, E) in meshes.items():
+        assert np.array_equal(m.params(), g[name + "_params"]), name
+        assert m.param() == g[name + "_params"].max()
+        assert np.array_equal(m.interior_nodes(), g[name + "_interior_nodes"])
+        assert np.array_equal(m.nodes_satisfying(low), g[name + "_nodes_low"])
+        assert np.array_equal(m.nodes_satisfying(low, boundaries_only=True),
+                              g[name + "_bnodes_low"])
+        assert np.array_equal(m.elements_satisfying(low), g[name + "_elements_low"])
+        ms = m.with_subdomains({"low": low, "pick": np.array([0, 2])})
+        assert m.subdomains is None and set(ms.subdomains) == {"low", "pick"}
+        assert np.array_equal(ms.normalize_elements(["low", "pick"]), g[name + "_norm_names"])
+        assert np.array_equal(ms.normalize_elements([4, 1, 1]), g[name + "_norm_list"])
+        assert np.array_equal(ms.normalize_elements(True), np.arange(m.t.shape[1]))
+        b = fem.Basis(ms, E(), elements="low")
+        assert np.array_equal(b.tind, g[name + "_sub_tind"])
+        assert b.nelems == int(g[name + "_sub_nelems"])
+        named = ms.with_boundaries({"left": lambda q: q[0] == 0.})
+        assert set(named.subdomains) == {"low", "pick"} and "left" in named.boundaries
+        with pytest.raises(ValueError, match="Subdomain 'top' not found."):
+            ms.normalize_elements("top")

@@ -27,8 +27,24 @@ def main():
     for name, m in cases.items():
         out[name + "_p"] = m.p
         out[name + "_t"] = m.t
+    # selections and mesh parameters (mesh.py:251-275,402-424,476-493, mesh_2d/3d.py params)
+    sel = {"tet": skfem.MeshTet.init_tensor(x, y, z), "tri": skfem.MeshTri().refined(3),
+           "hex": skfem.MeshHex.init_tensor(x, y, z)}
+    for name, m in sel.items():
+        ms = m.with_subdomains({"low": lambda q: q[0] < 0.5, "pick": np.array([0, 2])})
+        out[name + "_params"] = m.params()
+        out[name + "_interior_nodes"] = m.interior_nodes()
+        out[name + "_nodes_low"] = m.nodes_satisfying(lambda q: q[0] < 0.5)
+        out[name + "_bnodes_low"] = m.nodes_satisfying(lambda q: q[0] < 0.5, boundaries_only=True)
+        out[name + "_elements_low"] = m.elements_satisfying(lambda q: q[0] < 0.5)
+        out[name + "_norm_names"] = ms.normalize_elements(["low", "pick"])
+        out[name + "_norm_list"] = ms.normalize_elements([4, 1, 1])
+        basis = skfem.Basis(ms, {"tet": skfem.ElementTetP2, "tri": skfem.ElementTriP2,
+                                 "hex": skfem.ElementHex2}[name](), elements="low")
+        out[name + "_sub_tind"] = basis.tind
+        out[name + "_sub_nelems"] = basis.nelems
     np.savez_compressed(OUT, **out)
-    print("wrote", OUT, {k: v.shape for k, v in out.items()})
+    print("wrote", OUT, {k: np.shape(v) for k, v in out.items()})
 
 
 if __name__ == "__main__":
