@@ -142,6 +142,29 @@ class CellBasis(AbstractBasis):
         return type(self)(self.mesh, elem, mapping=self.mapping, quadrature=(self.X, self.W),
                           elements=self.tind)
 
+    def with_elements(self, elements):
+        """Same element and quadrature restricted to ``elements`` - anything
+        ``Mesh.normalize_elements`` accepts (cell_basis.py:266-280)."""
+        return type(self)(self.mesh, self.elem, mapping=self.mapping,
+                          quadrature=(self.X, self.W), elements=elements)
+
+    def boundary(self, facets=None, intorder=None, quadrature=None):
+        """The FacetBasis of the same mesh and element (cell_basis.py:282-308)."""
+        from .facet_basis import FacetBasis
+        if self.tind is not None:
+            raise NotImplementedError("Boundary of subdomain not supported.")
+        return FacetBasis(self.mesh, self.elem, mapping=self.mapping, facets=facets,
+                          intorder=intorder, quadrature=quadrature)
+
+    @property
+    def quadrature(self):
+        return self.X, self.W
+
+    def zero_w(self, dtype=None):
+        """Zero array of the shape forms see at the quadrature points
+        (abstract_basis.py:378-382)."""
+        return np.zeros((self.nelems, len(self.W)), dtype=dtype)
+
     def complement_dofs(self, *D):
         return np.setdiff1d(np.arange(self.N), np.concatenate([np.asarray(d).ravel() for d in D]))
 

@@ -243,3 +243,24 @@ def test_mesh_selections_parameters_and_ball_match_reference():
         assert set(named.subdomains) == {"low", "pick"} and "left" in named.boundaries
         with pytest.raises(ValueError, match="Subdomain 'top' not found."):
             ms.normalize_elements("top")
+
+
+def test_cell_basis_conveniences():
+    """with_elements / boundary / quadrature / zero_w (cell_basis.py:266-308,
+    abstract_basis.py:378-382): thin host-side constructors over tested primitives."""
+    m = fem.MeshTet.init_tensor(*(3 * (np.linspace(0, 1, 4),)))
+    b = fem.Basis(m, fem.ElementTetP2())
+    fb = b.boundary()
+    ref = fem.FacetBasis(m, fem.ElementTetP2())
+    assert isinstance(fb, fem.FacetBasis) and np.array_equal(fb.find, ref.find)
+    assert np.array_equal(fb.X, ref.X) and fb.mapping is b.mapping
+    left = b.boundary(lambda x: x[0] == 0., intorder=2)
+    assert np.array_equal(left.find, m.facets_satisfying(lambda x: x[0] == 0.))
+    assert np.array_equal(left.W, fem.FacetBasis(m, fem.ElementTetP2(), intorder=2).W)
+    sub = b.with_elements(lambda x: x[0] < 0.5)
+    assert np.array_equal(sub.tind, m.elements_satisfying(lambda x: x[0] < 0.5))
+    assert sub.quadrature[0] is not None and np.array_equal(sub.X, b.X)
+    assert np.array_equal(sub.element_dofs, b.element_dofs[:, sub.tind])
+    assert b.zero_w().shape == (m.t.shape[1], len(b.W)) and sub.zero_w().shape[0] == sub.nelems
+    with pytest.raises(NotImplementedError, match="Boundary of subdomain"):
+        sub.boundary()
