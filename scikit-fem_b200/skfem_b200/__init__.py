@@ -24,7 +24,8 @@ from .form import (Form, BilinearForm, LinearForm, Functional, COOData, DeviceCS
 from .utils import enforce, condense, solve, solver_iter_pcg
 from . import helpers, models, quadrature, utils
 
-InteriorBasis = CellBasis  # deprecated alias kept by the reference
+InteriorBasis = CellBasis  # deprecated aliases kept by the reference
+ExteriorFacetBasis = FacetBasis
 
 __version__ = "0.1.0"
 
@@ -33,7 +34,7 @@ __all__ = [
     "Element", "ElementH1", "ElementTriP1", "ElementTriP2", "ElementTetP1", "ElementTetP2",
     "ElementHex1", "ElementHex2", "ElementVector", "MappingAffine", "MappingIsoparametric",
     "Dofs", "get_quadrature", "AbstractBasis", "CellBasis", "Basis", "InteriorBasis",
-    "FacetBasis", "BoundaryFacetBasis", "InteriorFacetBasis",
+    "FacetBasis", "BoundaryFacetBasis", "ExteriorFacetBasis", "InteriorFacetBasis",
     "DiscreteField", "DeviceArray", "asdevice", "Form", "BilinearForm", "LinearForm",
     "Functional", "COOData", "DeviceCSR", "FormExtraParams", "asm", "helpers", "models",
     "enforce", "condense", "solve", "solver_iter_pcg", "utils",
