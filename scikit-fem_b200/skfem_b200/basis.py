@@ -127,14 +127,21 @@ class CellBasis(AbstractBasis):
         """DOFs on a set of facets (abstract_basis.py:124-237): ``facets`` is None (the
         whole boundary), an array of facet indices, a callable on facet midpoints, a
         boundary name or a list of those; a dict of names gives a dict of results.
-        Returns the sorted array the reference's ``DofsView.all()`` would."""
-        if elements is not None or nodes is not None or skip is not None:
-            raise NotImplementedError("get_dofs: only the `facets` selector is supported")
+        ``elements`` / ``nodes`` select by elements (anything ``normalize_elements`` takes) or
+        vertices instead; ``skip`` lists DOF names to leave out.  Returns a
+        :class:`~skfem_b200.dofs.DofsView`: array-like (sorted unique int32 indices) with
+        ``.all(name)``, ``.flatten()``, ``.keep / .drop``, ``.nodal / .facet / .edge /
+        .interior``."""
+        locs = (lambda: self.doflocs) if not self._disable_doflocs else None
         if isinstance(facets, dict):
-            return {k: self.get_dofs(v) for k, v in facets.items()}
-        if facets is None:
-            return self.dofs.boundary()
-        return self.dofs.on_facets(self.mesh.normalize_facets(facets))
+            return {k: self.get_dofs(v, skip=skip) for k, v in facets.items()}
+        if elements is not None:
+            return self.dofs.element_view(self.mesh.normalize_elements(elements), skip, locs)
+        if nodes is not None:
+            return self.dofs.vertex_view(self.mesh.normalize_nodes(nodes), skip, locs)
+        facets = (self.mesh.boundary_facets() if facets is None
+                  else self.mesh.normalize_facets(facets))
+        return self.dofs.facet_view(facets, skip, locs)
 
     def with_element(self, elem):
         """Same mesh, quadrature and element subset with another element

@@ -20,6 +20,113 @@ def _block(ndofs_per_entity, nentities, offset):
     return tab.reshape((ndofs_per_entity, nentities), order='F') + np.int32(offset)
 
 
+class DofsView:
+    """A subset of a :class:`Dofs` numbering - what ``basis.get_dofs(...)`` returns (the
+    reference's ``DofsView``, dofs.py:17-262).  It remembers *which* vertices / facets / edges /
+    cells were selected and which DOF rows of each are kept, so that the set can be narrowed
+    by name (``keep`` / ``drop`` / ``all('u^1')``) or split by entity type (``nodal`` ...).
+    Anything numpy-like (``np.asarray``, fancy indexing, ``len``, iteration) sees the sorted
+    unique DOF indices, an int32 array."""
+
+    KINDS = ("nodal", "facet", "edge", "interior")      # the order of ``element.dofnames``
+
+    def __init__(self, dofs, entities, rows=None, doflocs=None):
+        self.dofs = dofs
+        self.entities = {k: np.asarray(entities.get(k, np.zeros(0, np.int32))) for k in self.KINDS}
+        self.rows = rows if rows is not None else {k: list(range(self._table(k).shape[0]))
+                                                   for k in self.KINDS}
+        self._doflocs = doflocs                          # callable -> (dim, N) array, or None
+
+    # -- tables ------------------------------------------------------------------
+    def _table(self, kind):
+        return getattr(self.dofs, kind + "_dofs")
+
+    def _name_offset(self, kind):
+        return sum(self._table(k).shape[0] for k in self.KINDS[:self.KINDS.index(kind)])
+
+    def _selected(self, kind):
+        tab = self._table(kind)
+        if tab.size == 0 or len(self.rows[kind]) == 0:
+            return np.zeros((0, 0), dtype=np.int32)
+        return tab[self.rows[kind]][:, self.entities[kind]]
+
+    def _by_name(self, kind):
+        """{dof name: indices}; rows that share a name are concatenated row by row."""
+        if self._table(kind).size == 0:
+            return {}
+        names = self.dofs.element.dofnames
+        off, out = self._name_offset(kind), {}
+        sel = self._selected(kind)
+        for i, r in enumerate(self.rows[kind]):
+            row = sel[i] if sel.size else np.zeros(0, dtype=np.int32)
+            out.setdefault(names[off + r], []).append(row)
+        return {k: np.concatenate(v).astype(np.int32) for k, v in out.items()}
+
+    nodal = property(lambda self: self._by_name("nodal"))
+    facet = property(lambda self: self._by_name("facet"))
+    edge = property(lambda self: self._by_name("edge"))
+    interior = property(lambda self: self._by_name("interior"))
+
+    # -- the flat view -------------------------------------------------------------
+    def flatten(self):
+        parts = [self._selected(k).reshape(-1) for k in self.KINDS]
+        return np.unique(np.concatenate(parts)).astype(np.int32)
+
+    def all(self, key=None):
+        return self.flatten() if key is None else self.keep(key).flatten()
+
+    def __array__(self, dtype=None, copy=None):
+        flat = self.flatten()
+        return flat if dtype is None else flat.astype(dtype)
+
+    def __len__(self):
+        return len(self.flatten())
+
+    def __iter__(self):
+        return iter(self.flatten())
+
+    def __getitem__(self, ix):
+        return self.flatten()[ix]
+
+    def __repr__(self):
+        counts = ", ".join("{} {}".format(len(np.unique(self._selected(k))), k)
+                           for k in self.KINDS if self._selected(k).size)
+        return "<skfem_b200 DofsView({}): {} DOFs ({})>".format(
+            type(self.dofs.element).__name__, len(self), counts)
+
+    # -- narrowing by DOF name -----------------------------------------------------
+    def _filtered(self, dofnames, keep):
+        if isinstance(dofnames, str):
+            dofnames = [dofnames]
+        names = self.dofs.element.dofnames
+        rows = {k: [r for r in self.rows[k]
+                    if (names[self._name_offset(k) + r] in dofnames) == keep]
+                for k in self.KINDS}
+        return DofsView(self.dofs, self.entities, rows, self._doflocs)
+
+    def keep(self, dofnames):
+        """Only the DOFs with the given names, e.g. ``['u^1']``."""
+        return self._filtered(dofnames, True)
+
+    def drop(self, dofnames):
+        """Everything but the DOFs with the given names."""
+        return self._filtered(dofnames, False)
+
+    def sort(self, sorting=None):
+        """The DOF indices ordered by ``sorting(doflocs)`` (default: the coordinate sum)."""
+        if self._doflocs is None:
+            raise NotImplementedError("DofsView.sort needs the DOF locations of a basis")
+        flat = self.flatten()
+        x = self._doflocs()[:, flat]
+        return flat[np.argsort(sum(x) if sorting is None else sorting(x))]
+
+    def __or__(self, other):
+        ents = {k: np.union1d(self.entities[k], other.entities[k]) for k in self.KINDS}
+        return DofsView(self.dofs, ents, self.rows, self._doflocs)
+
+    __add__ = __or__
+
+
 class Dofs:
 
     def __init__(self, topo, element, offset=0):
@@ -87,3 +194,39 @@ class Dofs:
     def boundary(self):
         """All DOFs attached to boundary vertices / edges / facets."""
         return self.on_facets(self.topo.boundary_facets())
+
+    # -- views (dofs.py:536-663): which entities carry the selected DOFs ---------------
+    def _view(self, entities, skip, doflocs):
+        el = self.element
+        empty = np.zeros(0, dtype=np.int32)
+        ents = {"nodal": entities.get("nodal", empty) if el.nodal_dofs > 0 else empty,
+                "edge": entities.get("edge", empty) if self.edge_dofs.size else empty,
+                "facet": entities.get("facet", empty) if el.facet_dofs > 0 else empty,
+                "interior": entities.get("interior", empty)}
+        view = DofsView(self, ents, doflocs=doflocs)
+        return view.drop(skip) if skip else view
+
+    def facet_view(self, facets, skip=None, doflocs=None):
+        m = self.topo
+        facets = np.asarray(facets, dtype=np.int64)
+        ents = {"facet": facets}
+        if self.element.nodal_dofs > 0:
+            ents["nodal"] = np.unique(m.facets[:, facets])
+        if self.edge_dofs.size:
+            ents["edge"] = m.facet_edges(facets)
+        return self._view(ents, skip, doflocs)
+
+    def element_view(self, elements, skip=None, doflocs=None):
+        m = self.topo
+        elements = np.asarray(elements, dtype=np.int64)
+        ents = {"interior": elements}
+        if self.element.nodal_dofs > 0:
+            ents["nodal"] = np.unique(m.t[:, elements])
+        if self.edge_dofs.size:
+            ents["edge"] = np.unique(m.t2e[:, elements])
+        if self.element.facet_dofs > 0:
+            ents["facet"] = np.unique(m.t2f[:, elements])
+        return self._view(ents, skip, doflocs)
+
+    def vertex_view(self, nodes, skip=None, doflocs=None):
+        return self._view({"nodal": np.asarray(nodes, dtype=np.int64)}, skip, doflocs)

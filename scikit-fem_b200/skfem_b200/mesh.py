@@ -316,6 +316,20 @@ class Mesh:
         nodes = np.nonzero(test(self.p))[0].astype(np.int32)
         return np.intersect1d(nodes, self.boundary_nodes()) if boundaries_only else nodes
 
+    def normalize_nodes(self, nodes):
+        """Vertex indices from an index, an array, a test on vertex coordinates, a point given
+        as a tuple of coordinates, or a list / set of those (mesh.py:1259-1289)."""
+        if isinstance(nodes, tuple):
+            pt = np.array(list(nodes))[:, None]
+            return self.nodes_satisfying(lambda x: np.linalg.norm(x - pt, axis=0) < 1e-12)
+        if isinstance(nodes, np.ndarray):
+            return nodes
+        if isinstance(nodes, (list, set)):
+            return np.unique(np.concatenate([self.normalize_nodes(n) for n in nodes]))
+        if callable(nodes):
+            return self.nodes_satisfying(nodes)
+        raise NotImplementedError    # bare integers: like the reference, pass an array
+
     def elements_satisfying(self, test):
         """Elements whose midpoint (mean of the vertices) satisfies ``test``."""
         return np.nonzero(test(self.p[:, self.t].mean(axis=1)))[0].astype(np.int32)
