@@ -14,7 +14,7 @@ from .mesh import Mesh, MeshTri, MeshTet, MeshHex, MeshTri1, MeshTet1, MeshHex1
 from .element import (Element, ElementH1, ElementTriP1, ElementTriP2, ElementTetP1,
                       ElementTetP2, ElementHex1, ElementHex2, ElementVector)
 from .mapping import MappingAffine, MappingIsoparametric
-from .dofs import Dofs
+from .dofs import Dofs, DofsView
 from .quadrature import get_quadrature
 from .basis import AbstractBasis, CellBasis, Basis
 from .facet_basis import FacetBasis, BoundaryFacetBasis, InteriorFacetBasis
@@ -33,7 +33,7 @@ __all__ = [
     "Mesh", "MeshTri", "MeshTet", "MeshHex", "MeshTri1", "MeshTet1", "MeshHex1",
     "Element", "ElementH1", "ElementTriP1", "ElementTriP2", "ElementTetP1", "ElementTetP2",
     "ElementHex1", "ElementHex2", "ElementVector", "MappingAffine", "MappingIsoparametric",
-    "Dofs", "get_quadrature", "AbstractBasis", "CellBasis", "Basis", "InteriorBasis",
+    "Dofs", "DofsView", "get_quadrature", "AbstractBasis", "CellBasis", "Basis", "InteriorBasis",
     "FacetBasis", "BoundaryFacetBasis", "ExteriorFacetBasis", "InteriorFacetBasis",
     "DiscreteField", "DeviceArray", "asdevice", "Form", "BilinearForm", "LinearForm",
     "Functional", "COOData", "DeviceCSR", "FormExtraParams", "asm", "helpers", "models",
