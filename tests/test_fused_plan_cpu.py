@@ -142,6 +142,25 @@ def test_fused_plan_records_reproduce_the_csr(T, morph, tiling):
     assert st["sell_padding"] >= 1.0 and st["tile_slots_per_csr_slot"] >= 0.5
 
 
+@pytest.mark.parametrize("tiling", ["morton", "kd"])
+def test_fused_plan_on_an_unstructured_ball(tiling):
+    """Same emulation on MeshTet.init_ball(2): curved, unstructured, vertex valences up to
+    ~30 tets, so the F = 2 / 4 split lists and their shuffle-tree combination are exercised."""
+    import os
+    import skfem_b200 as fem
+    from skfem_b200 import _lib, fused
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    ball = fem.MeshTet.init_ball(2)
+    m = mesh_of(dict(p=ball.p, t=ball.t), "tet")
+    basis, plan, A = _plan_on_cpu(m)
+    fp = fused.build(basis, plan, T=128, tiling=tiling)
+    csr = _emulate(fp, m.p, 128)
+    assert not np.isnan(csr).any()
+    np.testing.assert_allclose(csr, A.data, rtol=1e-11, atol=1e-12 * np.abs(A.data).max())
+
+
 def test_kd_tiling_is_a_permutation_and_shares_fewer_slots():
     """fused._kd_order: every element exactly once, tiles = consecutive chunks of T, and on a
     Kuhn grid fewer canonical CSR slots are shared between tiles than with the Morton cut."""
