@@ -1,0 +1,103 @@
+"""Test infrastructure: run the two device-only plan passes of the fused path on the CPU.
+
+``csrc/skb_p1_plan.cu`` holds two kernels that rewrite the tile records in place (bank spreading
+of the P2 lists, conflict-free tile-local vertex ids).  Both are scalar per-thread code - one
+thread per half-group / per tile, no warp intrinsics, no shared memory - so the *same source* can
+be compiled by g++: this module cuts the kernels out of the .cu file (everything except the
+``extern "C"`` launchers), puts a few-line shim in front (``__global__`` -> nothing,
+``blockIdx`` / ``threadIdx`` as plain variables), adds host drivers that loop over the thread
+ids, and builds ``oracle/_build/libp1_plan_host.so``.  Nothing here is product code and nothing
+in the product calls it; the CPU tests use it to check that a plan is still a correct plan after
+the two passes (tests/test_fused_plan_cpu.py).
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "scikit-fem_b200", "csrc", "skb_p1_plan.cu")
+OUT_DIR = os.path.join(ROOT, "oracle", "_build")
+LIB = os.path.join(OUT_DIR, "libp1_plan_host.so")
+
+SHIM = r"""
+#include <cstdint>
+#include <cstring>
+#include <algorithm>
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__ __restrict
+using std::min;
+using std::max;
+struct idx3 { unsigned x, y, z; };
+static idx3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1};
+"""
+
+DRIVERS = r"""
+extern "C" void host_plan_spread(uint16_t *rec16, const int64_t *grp_pos, const int32_t *grp_len,
+                                 int64_t ngroups, int zero_base) {
+  for (int64_t t = 0; t < 2 * ngroups; ++t) {
+    blockIdx.x = (unsigned)t;
+    skb::p1_plan_spread_kernel(rec16, grp_pos, grp_len, ngroups, zero_base);
+  }
+}
+extern "C" void host_plan_renumber(unsigned char *rec, const uint64_t *rec_start, int ntiles,
+                                   int tile_elems) {
+  for (int t = 0; t < ntiles; ++t) {
+    blockIdx.x = (unsigned)t;
+    skb::p1_plan_renumber_kernel(rec, rec_start, ntiles, tile_elems);
+  }
+}
+"""
+
+
+def _host_source():
+    src = open(SRC).read()
+    src = src.replace('#include "skb_common.cuh"', "")
+    # drop the extern "C" launchers (<<<...>>> is not C++): from the keyword to the closing
+    # brace in column 0
+    src = re.sub(r'extern "C"[^\n]*\n(?:.*\n)*?\}\n', "", src)
+    return SHIM + src + DRIVERS
+
+
+def build():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    if os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(SRC),
+                                                            os.path.getmtime(__file__)):
+        return LIB
+    cpp = os.path.join(OUT_DIR, "p1_plan_host.cpp")
+    with open(cpp, "w") as f:
+        f.write(_host_source())
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                    "-o", LIB, cpp], check=True, capture_output=True)
+    return LIB
+
+
+def apply(fp, T, spread=True, renumber=True):
+    """Run the plan passes in place on the records of a plan built on CPU tensors."""
+    lib = C.CDLL(build())
+    rec = fp.rec.numpy()                       # int32 view of the record blob, shared memory
+    rs = np.ascontiguousarray(fp.rec_start.numpy().astype(np.uint64))
+    if spread:
+        pos, length = [], []
+        for tile in range(fp.ntiles):
+            base = int(rs[tile])
+            hdr = [int(v) & 0xFFFFFFFF for v in rec[base // 4: base // 4 + 8]]
+            ngroups, off_grp, off_ids = hdr[1], hdr[3], hdr[5]
+            grp = rec[(base + off_grp) // 4: (base + off_grp) // 4 + ngroups].view(np.uint32)
+            for g in grp:
+                pos.append((base + off_ids) // 2 + int(g & 0xFFFF) * 32)
+                length.append(int(g >> 16))
+        pos = np.asarray(pos, dtype=np.int64)
+        length = np.asarray(length, dtype=np.int32)
+        lib.host_plan_spread(C.c_void_p(rec.ctypes.data), C.c_void_p(pos.ctypes.data),
+                             C.c_void_p(length.ctypes.data), C.c_int64(len(pos)),
+                             C.c_int(10 * T))
+    if renumber:
+        lib.host_plan_renumber(C.c_void_p(rec.ctypes.data), C.c_void_p(rs.ctypes.data),
+                               C.c_int(fp.ntiles), C.c_int(T))
+    return fp

@@ -9,9 +9,11 @@ exactly as csrc/skb_p1_fused.cu does and emulates the kernel's two phases in num
          CSR slot / its mirror / the scratch position named by meta / meta2
     skb_p1_combine   per shared slot, the partials in tile order
 
-and compares the assembled values with the oracle's CSR.  (The two device-only
-plan passes - bank spreading and vertex renumbering - permute this layout in place
-and are covered by the GPU parity tests.)"""
+and compares the assembled values with the oracle's CSR.  The two device-only plan
+passes - bank spreading and vertex renumbering, csrc/skb_p1_plan.cu - permute this
+layout in place; their kernels are scalar per-thread code, so tests/host_plan_passes.py
+compiles the same source with g++ and the last test here checks that a plan is still
+a correct plan after them (and that they did what they are for)."""
 from types import SimpleNamespace
 
 import numpy as np
@@ -181,3 +183,72 @@ def test_kd_tiling_is_a_permutation_and_shares_fewer_slots():
     assert shared["kd"] < shared["morton"]
     with pytest.raises(ValueError):
         fused.build(basis, plan, T=512, tiling="hilbert")
+
+
+def _smem_passes(fp, T):
+    """Shared-memory passes (wavefronts) of P2's value gathers and of P1's coordinate
+    gathers under the calibrated model of tools/sim_smem_conflicts.py: an 8-byte access of
+    16 lanes costs max over the 16 bank pairs of the number of distinct words in the pair."""
+    rec = fp.rec.numpy()
+    rec16 = rec.view(np.uint16)
+    rs = fp.rec_start.numpy()
+
+    def cost(words):                       # words: (..., 16) -> passes per half-warp access
+        words = words.reshape(-1, 16).astype(np.int64)
+        out = 0
+        for row in words:
+            pairs = {}
+            for w in set(row.tolist()):
+                pairs[w & 15] = pairs.get(w & 15, 0) + 1
+            out += max(pairs.values())
+        return out
+    p1 = p2 = 0
+    for tile in range(fp.ntiles):
+        base = int(rs[tile])
+        hdr = [int(v) & 0xFFFFFFFF for v in rec[base // 4: base // 4 + 8]]
+        ngroups, off_grp, off_ids = hdr[1], hdr[3], hdr[5]
+        tl = rec16[(base + 32) // 2: (base + 32) // 2 + 4 * T].reshape(T, 4)
+        live = tl[:, 0] != 0xFFFF
+        for slot in range(4):
+            col = np.where(live, tl[:, slot], 0)
+            p1 += cost(col.reshape(-1, 16))
+        grp = rec[(base + off_grp) // 4: (base + off_grp) // 4 + ngroups].view(np.uint32)
+        for g in grp:
+            ln, off = int(g >> 16), int(g & 0xFFFF)
+            ids = rec16[(base + off_ids) // 2 + off * 32: (base + off_ids) // 2 + (off + ln) * 32]
+            p2 += cost(ids.reshape(ln, 2, 16))
+    return p1, p2
+
+
+@pytest.mark.parametrize("tiling", ["morton", "kd"])
+@pytest.mark.parametrize("shape", ["kuhn", "ball"])
+def test_plan_passes_keep_the_plan_correct_and_cut_bank_conflicts(shape, tiling):
+    import os
+    import skfem_b200 as fem
+    import host_plan_passes
+    from oracle import skfem_oracle as O
+    from skfem_b200 import _lib, fused
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    if shape == "kuhn":
+        g1 = np.linspace(0, 1, 8)
+        m = O.mesh_tet_tensor(g1, g1, g1)
+    else:
+        ball = fem.MeshTet.init_ball(2)
+        m = mesh_of(dict(p=ball.p, t=ball.t), "tet")
+    T = 256
+    basis, plan, A = _plan_on_cpu(m)
+    fp = fused.build(basis, plan, T=T, tiling=tiling)
+    p1_before, p2_before = _smem_passes(fp, T)
+    before = fp.rec.numpy().copy()
+    host_plan_passes.apply(fp, T)
+    assert (before != fp.rec.numpy()).any()
+    csr = _emulate(fp, m.p, T)
+    assert not np.isnan(csr).any()
+    np.testing.assert_allclose(csr, A.data, rtol=1e-11, atol=1e-12 * np.abs(A.data).max())
+    p1_after, p2_after = _smem_passes(fp, T)
+    assert p1_after < p1_before and p2_after < p2_before, (p1_before, p1_after,
+                                                            p2_before, p2_after)
+    print(shape, tiling, "P1 gathers", p1_before, "->", p1_after,
+          "P2 gathers", p2_before, "->", p2_after)
