@@ -8,7 +8,9 @@ be compiled by g++: this module cuts the kernels out of the .cu file (everything
 ``blockIdx`` / ``threadIdx`` as plain variables), adds host drivers that loop over the thread
 ids, and builds ``oracle/_build/libp1_plan_host.so``.  Nothing here is product code and nothing
 in the product calls it; the CPU tests use it to check that a plan is still a correct plan after
-the two passes (tests/test_fused_plan_cpu.py).
+the two passes (tests/test_fused_plan_cpu.py).  ``p1_combine_kernel`` - the second kernel of the
+warm step, a scalar grid-stride loop in csrc/skb_p1_fused.cu - is cut out and compiled the same
+way (``combine``), so the emulation's last stage runs the shipped source too.
 """
 import ctypes as C
 import os
@@ -19,6 +21,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "scikit-fem_b200", "csrc", "skb_p1_plan.cu")
+SRC_FUSED = os.path.join(ROOT, "scikit-fem_b200", "csrc", "skb_p1_fused.cu")
 OUT_DIR = os.path.join(ROOT, "oracle", "_build")
 LIB = os.path.join(OUT_DIR, "libp1_plan_host.so")
 
@@ -34,7 +37,8 @@ SHIM = r"""
 using std::min;
 using std::max;
 struct idx3 { unsigned x, y, z; };
-static idx3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1};
+static idx3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1},
+            gridDim = {1, 1, 1};
 """
 
 DRIVERS = r"""
@@ -52,6 +56,11 @@ extern "C" void host_plan_renumber(unsigned char *rec, const uint64_t *rec_start
     skb::p1_plan_renumber_kernel(rec, rec_start, ntiles, tile_elems);
   }
 }
+extern "C" void host_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
+                                const uint32_t *gslot2, int64_t nshared, double *csr_data) {
+  blockIdx.x = 0;                       // grid-stride loop: one "thread" walks every slot
+  skb::p1_combine_kernel(scratch, sptr, gslot, gslot2, nshared, csr_data);
+}
 """
 
 
@@ -61,13 +70,19 @@ def _host_source():
     # drop the extern "C" launchers (<<<...>>> is not C++): from the keyword to the closing
     # brace in column 0
     src = re.sub(r'extern "C"[^\n]*\n(?:.*\n)*?\}\n', "", src)
-    return SHIM + src + DRIVERS
+    # the second kernel of the warm step, cut out of the fused kernel's file (the fused kernel
+    # itself is TMA / mbarrier / cp.async PTX and stays GPU-only)
+    fused = open(SRC_FUSED).read()
+    m = re.search(r'__global__ void __launch_bounds__\(256\)\np1_combine_kernel\((?:.*\n)*?\}\n',
+                  fused)
+    combine = "namespace skb {\n" + m.group(0) + "}\n"
+    return SHIM + src + combine + DRIVERS
 
 
 def build():
     os.makedirs(OUT_DIR, exist_ok=True)
-    if os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(SRC),
-                                                            os.path.getmtime(__file__)):
+    if os.path.exists(LIB) and os.path.getmtime(LIB) >= max(
+            os.path.getmtime(SRC), os.path.getmtime(SRC_FUSED), os.path.getmtime(__file__)):
         return LIB
     cpp = os.path.join(OUT_DIR, "p1_plan_host.cpp")
     with open(cpp, "w") as f:
@@ -101,3 +116,14 @@ def apply(fp, T, spread=True, renumber=True):
         lib.host_plan_renumber(C.c_void_p(rec.ctypes.data), C.c_void_p(rs.ctypes.data),
                                C.c_int(fp.ntiles), C.c_int(T))
     return fp
+
+
+def combine(fp, scratch, csr):
+    """p1_combine_kernel (csrc/skb_p1_fused.cu) on the host: adds the per-tile partials in
+    ``scratch`` into ``csr`` (both float64 numpy arrays) following the plan's sptr / gslot."""
+    lib = C.CDLL(build())
+    sptr, gslot, gslot2 = (np.ascontiguousarray(x.numpy()) for x in (fp.sptr, fp.gslot, fp.gslot2))
+    lib.host_p1_combine(C.c_void_p(scratch.ctypes.data), C.c_void_p(sptr.ctypes.data),
+                        C.c_void_p(gslot.ctypes.data), C.c_void_p(gslot2.ctypes.data),
+                        C.c_int64(fp.nshared), C.c_void_p(csr.ctypes.data))
+    return csr

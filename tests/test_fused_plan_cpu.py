@@ -47,7 +47,7 @@ def _local_p1_laplace(X, w, nqp):
     return (g @ g.T) * abs(np.linalg.det(A)) * w * nqp
 
 
-def _emulate(fp, p, T):
+def _emulate(fp, p, T, host_combine=False):
     rec = fp.rec.numpy()
     rec16, rec8 = rec.view(np.uint16), rec.view(np.uint8)
     rs = fp.rec_start.numpy()
@@ -103,6 +103,9 @@ def _emulate(fp, p, T):
                     assert np.isnan(csr[m2])
                     csr[m2] = res
     # ---- skb_p1_combine ----
+    if host_combine:         # the real p1_combine_kernel source, compiled for the host
+        import host_plan_passes
+        csr_k = host_plan_passes.combine(fp, scratch.copy(), csr.copy())
     sptr, gslot, gslot2 = (x.numpy().view(np.uint32) for x in (fp.sptr, fp.gslot, fp.gslot2))
     for k in range(fp.nshared):
         acc = 0.0
@@ -114,6 +117,8 @@ def _emulate(fp, p, T):
             assert np.isnan(csr[gslot2[k]])
             csr[gslot2[k]] = acc
     assert not np.isnan(scratch[:fp.nscratch]).any()
+    if host_combine:
+        assert np.array_equal(csr_k, csr)             # bit for bit: same order of additions
     return csr
 
 
@@ -244,7 +249,7 @@ def test_plan_passes_keep_the_plan_correct_and_cut_bank_conflicts(shape, tiling)
     before = fp.rec.numpy().copy()
     host_plan_passes.apply(fp, T)
     assert (before != fp.rec.numpy()).any()
-    csr = _emulate(fp, m.p, T)
+    csr = _emulate(fp, m.p, T, host_combine=True)
     assert not np.isnan(csr).any()
     np.testing.assert_allclose(csr, A.data, rtol=1e-11, atol=1e-12 * np.abs(A.data).max())
     p1_after, p2_after = _smem_passes(fp, T)
