@@ -71,3 +71,43 @@ def test_local_kernels_match_reference_bitwise(name):
         assert np.array_equal(vec, g["unit_load_vec"]), name
         checked += 1
     assert checked > 0
+
+
+def _check_csr(plan, data, g, f):
+    assert np.array_equal(plan["indptr"], g[f + "_indptr"]), f
+    assert np.array_equal(plan["indices"], g[f + "_indices"]), f
+    ref = g[f + "_data"]
+    np.testing.assert_allclose(data, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", AFFINE)
+def test_generic_pipeline_on_the_cpu_matches_reference_csr(name):
+    """local kernel -> plan kernels (+ stable sort / scan) -> csr_reduce / vec_reduce, all from the
+    shipped sources compiled for the host (tests/host_local.py, tests/host_plan.py): indptr and
+    indices bit-exact, values within rtol 1e-12, load vectors bit-exact - the bar of
+    BASELINE.json's north_star, met without a GPU."""
+    import host_plan
+    refdom, ename, vector, bil, lin, has_local = CASES[name]
+    g = load(name)
+    basis = fem.Basis(mesh_from(g, refdom), element_from(ename, vector))
+    keep = []
+    sp = _space(basis, keep)
+    lib = host_local.lib()
+    nb, nel, N = basis.Nbfun, basis.nelems, basis.N
+    edofs = np.ascontiguousarray(basis.element_dofs)
+    for f in bil:
+        if f not in NATIVE:
+            continue
+        lam, two_mu = (LAME[0], 2. * LAME[1]) if f == "elasticity" else (1.0, 2.0)
+        local = np.full(nb * nb * nel, np.nan)
+        lib.host_local_affine(C.byref(sp), C.c_int(NATIVE[f][0]), C.c_double(lam),
+                              C.c_double(two_mu), C.c_void_p(local.ctypes.data), C.c_int(1),
+                              C.c_int(1 if vector else 0))
+        plan = host_plan.symbolic(local, edofs, edofs, nel, N, N, drop_zeros=True)
+        _check_csr(plan, host_plan.csr_reduce(local, plan), g, f)
+    if "unit_load" in lin and not vector:
+        local = np.full(nb * nel, np.nan)
+        lib.host_local_affine(C.byref(sp), C.c_int(_lib.LFORM_UNIT_LOAD), C.c_double(1.0),
+                              C.c_double(2.0), C.c_void_p(local.ctypes.data), C.c_int(0), C.c_int(0))
+        plan = host_plan.symbolic(None, edofs, None, nel, N, 1, drop_zeros=False)
+        assert np.array_equal(host_plan.vec_reduce(local, plan, N), g["unit_load_vec"])
