@@ -156,7 +156,10 @@ def run_gpu(args):
     _form.set_options(fused=not args.no_fused, fused_tile=args.tile, fused_threads=args.threads,
                       fused_ring=args.ring, fused_arith=args.arith,
                       fused_spread=not args.no_spread, fused_l2_persist=args.l2_persist,
-                      fused_renumber=not args.no_renumber, fused_tiling=args.tiling)
+                      fused_renumber=not args.no_renumber, fused_tiling=args.tiling,
+                      fused_version=args.fused_version, fused2_tile=args.tile2,
+                      fused2_ring=args.ring2, fused2_pool=args.pool, fused2_ctas=args.ctas,
+                      fused2_S=args.super_tiles)
     cells = args.cells
     da = None
     if world == 1:
@@ -336,9 +339,14 @@ def run_gpu(args):
     fused_stats = None
     for k, v in basis._plans.items():
         if isinstance(k, tuple) and k and k[0] in ("fused", "fused-mapped") and v is not None:
-            from skfem_b200 import fused as _fused
-            fused_stats = _fused.stats(v)
-            fused_stats["tile"], fused_stats["threads"], fused_stats["ring"] = v.T, v.threads, v.ring
+            if getattr(v, "version", 1) == 2:
+                from skfem_b200 import fused2 as _fused2
+                fused_stats = _fused2.stats(v)
+            else:
+                from skfem_b200 import fused as _fused
+                fused_stats = _fused.stats(v)
+                fused_stats["tile"], fused_stats["threads"], fused_stats["ring"] = \
+                    v.T, v.threads, v.ring
     algo_bytes = 4 * 4 * nel + 8 * 3 * nverts + 8 * nnz   # t + p + CSR data (warm)
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
     # DRAM traffic per step from the committed `ncu --set full` captures (same workload/path)
@@ -423,6 +431,14 @@ def main():
     ap.add_argument("--tiling", default="morton", choices=["morton", "kd"],
                     help="fused plan: how elements are cut into tiles (kd = compact k-d boxes, "
                          "opt-in until timed)")
+    ap.add_argument("--fused-version", type=int, default=2, dest="fused_version",
+                    help="2: super-tile / pool kernel (default), 1: first-generation kernel")
+    ap.add_argument("--tile2", type=int, default=256, help="v2: elements per tile = threads per CTA")
+    ap.add_argument("--ring2", type=int, default=3, help="v2: record buffers per CTA")
+    ap.add_argument("--pool", type=int, default=2048, help="v2: accumulators per super-tile")
+    ap.add_argument("--ctas", type=int, default=0, help="v2: CTAs per SM (0 = as many as fit)")
+    ap.add_argument("--super-tiles", type=int, default=None, dest="super_tiles",
+                    help="v2: tiles per super-tile (default: as many as the pool allows)")
     ap.add_argument("--tile", type=int, default=512)
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--threads", type=int, default=480,

@@ -1,0 +1,474 @@
+// Fused P1 (ElementTetP1) Laplace assembly, second generation: geometry -> local
+// matrix -> CSR values in one pass; element-local matrices never touch HBM.
+//
+// Replaces, for the headline path, the whole chain
+//   CellBasis.__init__           assembly/basis/cell_basis.py:94-106
+//   BilinearForm._assemble       assembly/form/bilinear_form.py:58-128,150-151
+//   COOData._assemble_scipy_csr  assembly/form/coo_data.py:27-36 (values)
+// for form = models/poisson.py:7-9 (laplace) on ElementTetP1.
+//
+// Plan (skfem_b200/fused2.py).  Elements are ordered by a balanced k-d tree into
+// *super-tiles* (compact boxes of S tiles) of *tiles* (T elements).  Every tile owns
+// one contiguous 16-byte aligned record in HBM (one TMA bulk copy):
+//     header | tl: T x ushort4 tile-local vertex ids (+ the expected zero mask of the
+//     10 unique local entries in the spare bits) | verts: global vertex ids |
+//     grp: per 32-lane group {offset, length} | lane: per lane the pool index of its
+//     slot | ids: sliced-ELL staging indices, two per 32-bit word
+// and every super-tile a flush table {CSR slot | scratch position, mirror slot} per
+// accumulator of its *pool*.
+//
+// Kernel: persistent CTAs, several per SM, each walking whole super-tiles:
+//   TMA    records are prefetched NR-1 tiles ahead (cp.async.bulk + mbarrier);
+//   LDGSTS the vertex coordinates of tile k+1 are gathered (cp.async) while tile k
+//          is reduced;
+//   P1     one element per thread: the 10 unique local entries in registers, bit
+//          identical to numpy, staged  vals[k*T + e]; the zero
+//          mask of the entries is compared with the plan's (pattern validation);
+//   P2     one lane per tile slot adds that slot's staged contributions in a fixed
+//          order and accumulates into the super-tile's pool in shared memory;
+//   flush  after the last tile of a super-tile the pool is written out in CSR order
+//          (coalesced runs): slots complete inside the super-tile go to csr_data (and
+//          their mirror), the others to a scratch array that skb_p1_combine adds in
+//          super-tile order.
+// No float atomics: results are bit-reproducible run to run.
+#include <cstdio>
+#include <cstring>
+#include "skb_common.cuh"
+
+namespace skb {
+
+struct P1v2Args {
+  const double *p;
+  int64_t npts;
+  const unsigned char *rec;     // concatenated tile records
+  const uint64_t *rec_start;    // [ntiles+1] byte offsets (multiples of 16)
+  const int32_t *st_tile0;      // [nst+1] first tile of every super-tile
+  const int64_t *st_fl0;        // [nst+1] first flush entry of every super-tile
+  const uint2 *fl;              // flush table: {target, mirror target}
+  int32_t nst;
+  int32_t rec_cap;              // largest record, bytes (multiple of 16)
+  int32_t vcap;                 // most vertices in one tile (even)
+  int32_t pool_cap;             // most accumulators in one super-tile (even)
+  int32_t ring;                 // record buffers
+  double *csr_data;
+  double *scratch;
+  double w;                     // the common quadrature weight
+  int32_t nqp;
+  int32_t debug;
+  int32_t *flag;                // device int: bit0 set when the zero mask of an element changed
+  uint16_t *nz_out;             // plan time only: receives the zero mask of every element
+};
+
+struct RecHeader2 {             // 32 bytes at the start of every record
+  uint32_t nverts, ngroups, off_verts, off_grp, off_lane, off_ids, nelems, pad;
+};
+
+// ---- async-copy / mbarrier primitives (PTX) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32_2(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init2(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32_2(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx2(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32_2(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait2(uint64_t *bar, unsigned parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32_2(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait2(uint64_t *bar, unsigned parity) {
+  while (!mbar_try_wait2(bar, parity)) {
+  }
+}
+// TMA bulk copy global -> shared, completion counted on an mbarrier; evict-first in L2 (the
+// records are read once per step)
+__device__ __forceinline__ void tma_bulk_g2s2(void *dst, const void *src, unsigned bytes,
+                                              uint64_t *bar) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32_2(dst)), "l"(src), "r"(bytes), "r"(smem_u32_2(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async8_2(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32_2(dst)), "l"(src)
+               : "memory");
+}
+
+__device__ __forceinline__ unsigned nonzero_bits(double v) {   // v != +-0, integer pipe only
+  return (((unsigned)__double2hiint(v) << 1) | (unsigned)__double2loint(v)) != 0u;
+}
+
+// walks the tiles of the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+struct TileCursor {
+  int st, tile, end;
+};
+
+// MODE 0: any mesh, any equal-weight rule: IEEE division, numpy's quadrature sum evaluated
+//         term by term.
+// MODE 1: nqp == 4, coordinates within the exact_div-safe range (P1FusedPlan.tame >= 1): one
+//         reciprocal + Markstein corrections per quotient (skb_common.cuh exact_div).
+// MODE 2: additionally coordinates within [2^-28, 2^28] and the weight within [2^-20, 1]: then
+//         d * dx is a normal number or exactly 0 for every entry, so numpy's
+//         ((v + v) + v) + v  (v = d * dx) equals 4 v = d * (4 dx) bit for bit - one
+//         multiplication instead of three operations (proof in DESIGN.md).
+// MODE 3: opt-in fast arithmetic (FMA + one reciprocal; values within a few ulp per term).
+template <int T, int MODE>
+__global__ void __launch_bounds__(T)
+p1tet_laplace_fused2_kernel(const P1v2Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int VSTRIDE = 10 * T + 16;   // + one staged 0.0 per bank pair
+  double *vals = reinterpret_cast<double *>(smem_raw);             // [VSTRIDE]
+  double *coords = vals + VSTRIDE;                                 // [3][vcap]
+  double *pool = coords + 3 * (size_t)a.vcap;                      // [pool_cap]
+  unsigned char *recs = reinterpret_cast<unsigned char *>(pool + a.pool_cap);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(recs + (size_t)a.ring * a.rec_cap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = T / 32;
+  const int NR = a.ring;
+
+  auto start = [&](TileCursor &c, int st) {
+    c.st = st;
+    if (st < a.nst) { c.tile = a.st_tile0[st]; c.end = a.st_tile0[st + 1]; }
+    else { c.tile = -1; c.end = -1; }
+  };
+  auto advance = [&](TileCursor &c) {
+    if (c.tile < 0) return;
+    if (++c.tile >= c.end) start(c, c.st + (int)gridDim.x);
+  };
+  auto rec_of = [&](int it) { return recs + (size_t)(it % NR) * a.rec_cap; };
+  auto issue = [&](int it, const TileCursor &c) {     // one thread: fetch the record of c.tile
+    if (c.tile < 0) return;
+    const uint64_t b0 = a.rec_start[c.tile];
+    const unsigned bytes = (unsigned)(a.rec_start[c.tile + 1] - b0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx2(&mbar[it % NR], bytes);
+    tma_bulk_g2s2(rec_of(it), a.rec + b0, bytes, &mbar[it % NR]);
+  };
+  auto wait_rec = [&](int it) { mbar_wait2(&mbar[it % NR], (unsigned)((it / NR) & 1)); };
+  auto gather = [&](int it) {   // async gather of the vertex coordinates of the tile in slot it
+    const unsigned char *r = rec_of(it);
+    const RecHeader2 *h = reinterpret_cast<const RecHeader2 *>(r);
+    const int nv = (int)h->nverts;
+    const int32_t *verts = reinterpret_cast<const int32_t *>(r + h->off_verts);
+    double *dx = coords, *dy = dx + a.vcap, *dz = dy + a.vcap;
+    const double *px = a.p, *py = a.p + a.npts, *pz = a.p + 2 * a.npts;
+    for (int i = tid; i < nv; i += T) {
+      const int32_t gv = verts[i];
+      cp_async8_2(dx + i, px + gv);
+      cp_async8_2(dy + i, py + gv);
+      cp_async8_2(dz + i, pz + gv);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < NR; ++i) mbar_init2(&mbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < 16; ++i) vals[10 * T + i] = 0.0;
+  }
+  __syncthreads();
+  TileCursor cur, pre;
+  start(cur, (int)blockIdx.x);
+  if (cur.tile < 0) return;
+  pre = cur;
+  int it_pre = 0;
+  if (tid == 0) {                       // prologue: NR records in flight
+    for (; it_pre < NR; ++it_pre) { issue(it_pre, pre); advance(pre); }
+  }
+  wait_rec(0);
+  gather(0);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  const double w1 = a.w;
+  const double w4 = a.w * 4.0;
+  unsigned bad = 0;
+  for (int it = 0; cur.tile >= 0; ++it) {
+    const unsigned char *r = rec_of(it);
+    const RecHeader2 *h = reinterpret_cast<const RecHeader2 *>(r);
+    // ---- P1: local matrix of element `tid` -> vals -------------------------------------
+    if (!(a.debug & 1)) {
+      const ushort4 v = reinterpret_cast<const ushort4 *>(r + sizeof(RecHeader2))[tid];
+      if (v.x != 0xFFFF) {   // not a padding element of a short tile
+        const int i0 = v.x & 0x3ff, i1 = v.y & 0x3ff, i2 = v.z & 0x3ff, i3 = v.w & 0x3ff;
+        const unsigned keep = (unsigned)(v.x >> 10) | ((unsigned)(v.y >> 10) << 6);
+        const double *sx = coords, *sy = sx + a.vcap, *sz = sy + a.vcap;
+        double A[3][3];
+        {
+          const double x0 = sx[i0], y0 = sy[i0], z0 = sz[i0];
+          A[0][0] = sx[i1] - x0; A[0][1] = sx[i2] - x0; A[0][2] = sx[i3] - x0;
+          A[1][0] = sy[i1] - y0; A[1][1] = sy[i2] - y0; A[1][2] = sy[i3] - y0;
+          A[2][0] = sz[i1] - z0; A[2][1] = sz[i2] - z0; A[2][2] = sz[i3] - z0;
+        }
+        double det, n[3][3], inv[3][3];
+        if (MODE == 3) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {   // cofactors, same sign convention as cofactors3
+            const int i1_ = (i + 1) % 3, i2_ = (i + 2) % 3;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+              n[j][i] = __fma_rn(A[i1_][j1], A[i2_][j2], -(A[i1_][j2] * A[i2_][j1]));
+            }
+          }
+          det = __fma_rn(A[0][0], n[0][0], __fma_rn(A[0][1], n[1][0], A[0][2] * n[2][0]));
+          const double y = 1.0 / det;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) inv[i][j] = n[i][j] * y;
+        } else {
+          // minors of the first row are shared between det (mapping_affine.py:92-98) and the
+          // first column of the inverse (:111-129): -b + a == a - b and b - a == -(a - b)
+          // bit for bit
+          const double m0 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+          const double m1 = A[1][0] * A[2][2] - A[1][2] * A[2][0];
+          const double m2 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+          det = A[0][0] * m0 - A[0][1] * m1 + A[0][2] * m2;
+          n[0][0] = m0;
+          n[1][0] = -m1;
+          n[2][0] = m2;
+          n[0][1] = A[0][2] * A[2][1] - A[0][1] * A[2][2];
+          n[1][1] = -A[0][2] * A[2][0] + A[0][0] * A[2][2];
+          n[2][1] = A[0][1] * A[2][0] - A[0][0] * A[2][1];
+          n[0][2] = -A[0][2] * A[1][1] + A[0][1] * A[1][2];
+          n[1][2] = A[0][2] * A[1][0] - A[0][0] * A[1][2];
+          n[2][2] = -A[0][1] * A[1][0] + A[0][0] * A[1][1];
+          if (MODE >= 1 && det != 0.0) {
+            const double y = __drcp_rn(det);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) inv[i][j] = exact_div(n[i][j], det, y);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) inv[i][j] = n[i][j] / det;
+          }
+        }
+        // P1 push-forward: dphi_b is +-unit, so grad_b (b=1..3) is row b-1 of inv and
+        // grad_0[j] = -((inv0j + inv1j) + inv2j)   (Appendix A.4)
+        double g[4][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          g[0][j] = -((inv[0][j] + inv[1][j]) + inv[2][j]);
+          g[1][j] = inv[0][j];
+          g[2][j] = inv[1][j];
+          g[3][j] = inv[2][j];
+        }
+        const double adet = fabs(det);
+        const double dx = adet * w1;            // cell_basis.py:104-105
+        const double dx4 = adet * w4;           // == 4 * dx exactly (power-of-two scaling)
+        unsigned nz = 0;
+        int k = 0;
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+          for (int q = pp; q < 4; ++q, ++k) {
+            double val;
+            if (MODE == 3) {
+              const double d = __fma_rn(g[pp][2], g[q][2],
+                                        __fma_rn(g[pp][1], g[q][1], g[pp][0] * g[q][0]));
+              val = d * dx4;
+            } else {
+              const double d = (g[pp][0] * g[q][0] + g[pp][1] * g[q][1]) + g[pp][2] * g[q][2];
+              if (MODE == 2) {
+                val = d * dx4;
+              } else if (MODE == 1) {
+                const double t = d * dx;
+                val = __fma_rn(t, 2.0, t) + t;   // (t+t)+t in one rounding, then + t
+              } else {
+                const double t = d * dx;
+                auto f = [&](int) -> double { return t; };
+                val = pw_sum(a.nqp, f);
+              }
+            }
+            nz |= nonzero_bits(val) << k;
+            vals[k * T + tid] = val;
+          }
+        bad |= (nz ^ keep);
+        if (a.nz_out) a.nz_out[(size_t)cur.tile * T + tid] = (uint16_t)nz;
+      }
+    }
+    // the record of the next tile has been in flight for at least NR - 1 iterations
+    TileCursor nxt = cur;
+    advance(nxt);
+    if (tid == 0 && nxt.tile >= 0) wait_rec(it + 1);
+    __syncthreads();   // (A) vals complete; record it+1 visible to everybody; coords free
+    if (nxt.tile >= 0) gather(it + 1);
+    // ---- P2: per-slot sums in fixed order (sliced ELL), accumulated into the pool ---------
+    if (!(a.debug & 2)) {
+      const int ngroups = (int)h->ngroups;
+      const uint32_t *grp = reinterpret_cast<const uint32_t *>(r + h->off_grp);
+      const uint16_t *lanew = reinterpret_cast<const uint16_t *>(r + h->off_lane);
+      const uint32_t *ids = reinterpret_cast<const uint32_t *>(r + h->off_ids);
+#pragma unroll 1
+      for (int gi = warp; gi < ngroups; gi += NW) {
+        const uint32_t gw = grp[gi];
+        const int rows = (int)(gw >> 16);                  // two ELL columns per row
+        const uint32_t *cb = ids + (size_t)(gw & 0xffffu) * 32 + lane;
+        const unsigned lw = lanew[gi * 32 + lane];
+        double acc = 0.0;
+#pragma unroll 2
+        for (int c = 0; c < rows; ++c) {
+          const uint32_t w2 = cb[c * 32];
+          const double a0 = vals[w2 & 0xffffu], a1 = vals[w2 >> 16];
+          acc = acc + a0;
+          acc = acc + a1;
+        }
+        // long lists are split over 2 or 4 adjacent lanes: fixed combination tree
+        // (l + l+1) + (l+2 + l+3), selected by the leader lane
+        const double t1 = acc + __shfl_down_sync(0xffffffffu, acc, 1);
+        const double t2 = t1 + __shfl_down_sync(0xffffffffu, t1, 2);
+        if (lw != 0xFFFFu) {
+          const unsigned fs = (lw >> 13) & 3u;
+          acc = fs == 0 ? acc : (fs == 1 ? t1 : t2);
+          const unsigned pi = lw & 0x1fffu;
+          if (lw & 0x8000u) pool[pi] = acc;                // first tile of the super-tile touching it
+          else pool[pi] = pool[pi] + acc;
+        }
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();   // (B) vals, record `it` free; coords of the next tile visible; pool updated
+    if (tid == 0) { issue(it_pre, pre); advance(pre); ++it_pre; }
+    // ---- flush: the super-tile's pool -> csr_data / scratch, in CSR order --------------------
+    if (nxt.st != cur.st) {
+      const int64_t f0 = a.st_fl0[cur.st];
+      const int np = (int)(a.st_fl0[cur.st + 1] - f0);
+      if (!(a.debug & 64)) {
+        for (int i = tid; i < np; i += T) {
+          const uint2 m = __ldcs(a.fl + f0 + i);
+          const double val = pool[i];
+          if (m.x & 0x80000000u) a.scratch[m.x & 0x7fffffffu] = val;
+          else a.csr_data[m.x] = val;
+          if (m.y != 0xffffffffu) a.csr_data[m.y] = val;
+        }
+      }
+      // the next super-tile's first pool write comes after barrier (A) of its first tile
+    }
+    cur = nxt;
+  }
+  if (bad & 0x3ffu) atomicOr(a.flag, 1);
+}
+
+__global__ void __launch_bounds__(256)
+p1_combine2_kernel(const double *__restrict__ scratch, const uint32_t *__restrict__ sptr,
+                   const uint32_t *__restrict__ gslot, const uint32_t *__restrict__ gslot2,
+                   int64_t nshared, double *__restrict__ csr_data) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nshared;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t a = sptr[k], b = sptr[k + 1];
+    double acc = scratch[a];
+    for (uint32_t i = a + 1; i < b; ++i) acc = acc + scratch[i];
+    const uint32_t s = gslot[k], s2 = gslot2[k];
+    csr_data[s] = acc;
+    if (s2 != s) csr_data[s2] = acc;   // mirror slot of a symmetric pair
+  }
+}
+
+template <int T, int MODE>
+static int launch_fused2(const P1v2Args &a, size_t smem, int sms, int ctas_per_sm,
+                         cudaStream_t st) {
+  auto k = p1tet_laplace_fused2_kernel<T, MODE>;
+  SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  SKB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T, smem));
+  if (occ < 1) return SKB_ETOOBIG;
+  if (ctas_per_sm > 0 && occ > ctas_per_sm) occ = ctas_per_sm;
+  int free_sms = sm_reserve();
+  if (free_sms > sms - 1) free_sms = sms - 1;
+  const int cap = occ * (sms - free_sms);
+  const int grid = a.nst < cap ? a.nst : cap;
+  k<<<grid, T, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace skb
+
+extern "C" int64_t skb_p1_fused2_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap,
+                                            int32_t vcap, int32_t pool_cap) {
+  return (int64_t)(sizeof(double) * ((10 * (size_t)tile_elems + 16) + 3 * (size_t)vcap +
+                                     (size_t)pool_cap) +
+                   (size_t)ring * rec_cap + 8 * (size_t)ring + 32);
+}
+
+// Warm fused P1-tet Laplace assembly (see the top of this file).  mode: 0 generic, 1 exact
+// division via reciprocal (tame coordinates, nqp == 4), 2 additionally the 4 * dx shortcut,
+// 3 fast (FMA) arithmetic.  `flag` (device int32) gets bit 0 set if the zero mask of any
+// element's local matrix differs from the plan's: the cached CSR pattern is then no longer the
+// reference's pattern and the caller must re-plan (coo_data.py:35, eliminate_zeros).
+// nz_out != NULL (plan time): only the local matrices are formed and the 10-bit zero mask of
+// element e of tile t is stored at nz_out[t * tile_elems + e]; nothing else is written.
+extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
+                                        const uint64_t *rec_start, const int32_t *st_tile0,
+                                        const int64_t *st_fl0, const void *fl, int32_t nst,
+                                        int32_t tile_elems, int32_t ring, int32_t rec_cap,
+                                        int32_t vcap, int32_t pool_cap, int32_t ctas_per_sm,
+                                        int32_t mode, double w, int32_t nqp, double *csr_data,
+                                        double *scratch, int32_t *flag, uint16_t *nz_out,
+                                        void *stream) {
+  using namespace skb;
+  if (nst < 0 || !p || nqp <= 0 || vcap <= 0 || (vcap & 1) || pool_cap <= 0 || (pool_cap & 1) ||
+      rec_cap <= 0 || (rec_cap & 15) || ring < 2 || ring > 8 || !flag)
+    return SKB_EINVAL;
+  if (mode < 0 || mode > 3 || ((mode == 1 || mode == 2) && nqp != 4)) return SKB_EINVAL;
+  if (nst == 0) return SKB_OK;
+  P1v2Args a;
+  a.p = p; a.npts = npts; a.rec = (const unsigned char *)rec; a.rec_start = rec_start;
+  a.st_tile0 = st_tile0; a.st_fl0 = st_fl0; a.fl = (const uint2 *)fl; a.nst = nst;
+  a.rec_cap = rec_cap; a.vcap = vcap; a.pool_cap = pool_cap; a.ring = ring;
+  a.csr_data = csr_data; a.scratch = scratch; a.w = w; a.nqp = nqp;
+  a.debug = debug_flags(); a.flag = flag; a.nz_out = nz_out;
+  if (nz_out) a.debug |= 2 | 64;     // plan-time mask pass: local matrices only
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = (size_t)skb_p1_fused2_smem_bytes(tile_elems, ring, rec_cap, vcap, pool_cap);
+  if (smem > 227 * 1024) return SKB_ETOOBIG;
+  int rc = SKB_EINVAL;
+#define SKB_P1V2_CASE(TT)                                                                \
+  if (tile_elems == TT) {                                                                \
+    if (mode == 0) rc = launch_fused2<TT, 0>(a, smem, sms, ctas_per_sm, st);             \
+    else if (mode == 1) rc = launch_fused2<TT, 1>(a, smem, sms, ctas_per_sm, st);        \
+    else if (mode == 2) rc = launch_fused2<TT, 2>(a, smem, sms, ctas_per_sm, st);        \
+    else rc = launch_fused2<TT, 3>(a, smem, sms, ctas_per_sm, st);                       \
+  }
+  SKB_P1V2_CASE(128)
+  SKB_P1V2_CASE(256)
+  SKB_P1V2_CASE(512)
+#undef SKB_P1V2_CASE
+  if (rc == SKB_OK) count_launch();
+  return rc;
+}
+
+extern "C" int skb_p1_combine2(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
+                               const uint32_t *gslot2, int64_t nshared, double *csr_data,
+                               void *stream) {
+  using namespace skb;
+  if (nshared < 0) return SKB_EINVAL;
+  if (nshared == 0) return SKB_OK;
+  int64_t g = (nshared + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  p1_combine2_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(scratch, sptr, gslot, gslot2,
+                                                               nshared, csr_data);
+  count_launch();
+  return (int)cudaGetLastError();
+}

@@ -241,6 +241,41 @@ class CellBasis(AbstractBasis):
         self._devcache[key] = d
         return d
 
+    def update_points(self, p, host=True):
+        """Move the mesh: new vertex coordinates ``p`` (``(dim, npts)`` numpy array or device
+        tensor), same connectivity.  The reference has no such call - a moved mesh is a new
+        ``Mesh`` + ``Basis`` (e.g. inside the Newton / time loops of docs/examples/ex10.py-style
+        scripts) and every assembly re-derives DOFs, tables and the sparsity pattern.  Here
+        the device copy of ``p`` is overwritten in place (all plans keep their pointers, a
+        captured CUDA graph stays valid), cached geometry fields are dropped, and sparsity
+        plans survive only where the next assembly can *validate* them: the fused P1 path
+        compares the zero mask of every local matrix with the plan's and re-plans when the
+        value-dependent pattern (coo_data.py:35) may have changed; all other cached plans are
+        discarded, so those forms take the cold path once.  ``host=False`` skips refreshing
+        ``mesh.p`` (the host copy then lags behind until the next call with ``host=True``)."""
+        torch = _torch()
+        d = self._dev()
+        src = p if torch.is_tensor(p) else torch.from_numpy(
+            np.ascontiguousarray(p, dtype=np.float64))
+        if tuple(src.shape) != tuple(d["p"].shape):
+            raise ValueError("update_points: expected an array of shape {}".format(
+                tuple(d["p"].shape)))
+        d["p"].copy_(src, non_blocking=True)
+        if host:
+            self.mesh.p[...] = src.cpu().numpy() if torch.is_tensor(p) else p
+        self._fields.clear()
+        if hasattr(self, "_doflocs"):
+            del self._doflocs
+        from . import fused2
+        keep = {}
+        for k, fp in self._plans.items():
+            if isinstance(k, tuple) and k and k[0] == "fused" and getattr(fp, "version", 1) == 2:
+                fp.mode = fused2.arithmetic_mode(d["p"], fp.w, fp.nqp)
+                fp.unchecked = True
+                keep[k] = fp
+                keep[k[1]] = self._plans[k[1]]
+        self._plans = keep
+
     @staticmethod
     def _stream():
         return C.c_void_p(_torch().cuda.current_stream().cuda_stream)

@@ -61,9 +61,14 @@ def _torch():
 #                     fused_tile elements; "kd": compact boxes from a balanced k-d tree
 #                     (fused._kd_order; fewer CSR slots shared between tiles - plan-only
 #                     change, not yet timed on a B200, hence opt-in)
+#   fused_version    2: super-tile / pool kernel (csrc/skb_p1_fused2.cu, fused2.py; options
+#                     fused2_tile, fused2_ring, fused2_pool, fused2_ctas, fused2_S);
+#                     1: the first-generation warp-specialised kernel (options above)
 _CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring": 4,
            "fused_arith": "exact", "fused_spread": True, "fused_renumber": True,
-           "fused_l2_persist": True, "fused_tiling": "morton"}
+           "fused_l2_persist": True, "fused_tiling": "morton",
+           "fused_version": 2, "fused2_tile": 256, "fused2_ring": 3, "fused2_pool": 2048,
+           "fused2_ctas": 0, "fused2_S": None}
 
 
 def set_options(**kw):
@@ -146,6 +151,11 @@ class DeviceCSR:
 
     def matvec(self, x):
         return self.to_torch() @ x
+
+
+class PatternChanged(RuntimeError):
+    """A warm re-assembly found local entries whose zero / nonzero status differs from the
+    cached plan's: the reference would produce another CSR pattern (coo_data.py:35)."""
 
 
 class Plan:
@@ -458,6 +468,16 @@ class BilinearForm(Form):
                 fkey = ("fused", key) if slot_map is None else ("fused-mapped", key,
                                                                 id(slot_map))
                 fp = ubasis._plans.get(fkey, False)
+                if fp is False and int(_CONFIG["fused_version"]) == 2:
+                    from . import fused2
+                    fp = fused2.build_auto(ubasis, plan, T=int(_CONFIG["fused2_tile"]),
+                                           ring=int(_CONFIG["fused2_ring"]),
+                                           pool_cap=int(_CONFIG["fused2_pool"]),
+                                           S=_CONFIG["fused2_S"], slot_map=slot_map,
+                                           spread=bool(_CONFIG["fused_spread"]),
+                                           renumber=bool(_CONFIG["fused_renumber"]),
+                                           ctas_per_sm=int(_CONFIG["fused2_ctas"]))
+                    ubasis._plans[fkey] = fp
                 if fp is False:
                     fp = fused.build_auto(ubasis, plan, T=fused_tile(),
                                           threads=int(_CONFIG["fused_threads"]),
@@ -469,8 +489,24 @@ class BilinearForm(Form):
                 if fp is not None:
                     data = out if out is not None else torch.empty(
                         plan.nnz, dtype=torch.float64, device=fp.p.device)
-                    fused.run(fp, data, _stream(), fast=_CONFIG["fused_arith"] == "fast",
-                              l2_persist=bool(_CONFIG["fused_l2_persist"]))
+                    if getattr(fp, "version", 1) == 2:
+                        from . import fused2
+                        fused2.run(fp, data, _stream(), fast=_CONFIG["fused_arith"] == "fast")
+                        # first run after basis.update_points: did the zero mask of any local
+                        # matrix change?  Then this pattern is no longer the reference's.
+                        if getattr(fp, "unchecked", False) and \
+                                not torch.cuda.is_current_stream_capturing():
+                            fp.unchecked = False
+                            if fused2.pattern_changed(fp):
+                                if out is not None:
+                                    raise PatternChanged(
+                                        "the sparsity pattern changed with the new vertex "
+                                        "coordinates: assemble once without out=")
+                                del ubasis._plans[fkey], ubasis._plans[key]
+                                return self.assemble_device(ubasis, vbasis)
+                    else:
+                        fused.run(fp, data, _stream(), fast=_CONFIG["fused_arith"] == "fast",
+                                  l2_persist=bool(_CONFIG["fused_l2_persist"]))
                     return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
         local = self._local(ubasis, vbasis, **kwargs)
         if plan is None:

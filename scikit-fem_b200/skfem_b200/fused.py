@@ -59,14 +59,16 @@ def _spread10(v):
     return v
 
 
-def _kd_order(corner, T):
+def _kd_order(corner, T, order=None, seg_cnt=None):
     """Element order whose consecutive chunks of T are compact boxes: a balanced k-d tree
     over the elements' bounding-box corners, every split placed after a whole number of tiles
     (left child = floor(k/2) full tiles), sorted along the segment's longest axis with the
     other two axes as tie-breakers.  All levels are processed at once with segmented sorts
     (two stable argsorts per level, ~log2(ntiles) levels).  Compared with cutting a Morton
     curve every T elements this leaves fewer CSR slots shared between tiles (C2: 49 % instead
-    of 65 % of the canonical slots, 29 % fewer per-tile partials; tools/store_sectors.py)."""
+    of 65 % of the canonical slots, 29 % fewer per-tile partials; tools/store_sectors.py).
+    ``order`` / ``seg_cnt`` (optional): start from this element order already cut into
+    segments of these sizes and refine every segment separately (nested tilings)."""
     torch = _torch()
     dev = corner.device
     i64 = torch.int64
@@ -75,10 +77,11 @@ def _kd_order(corner, T):
     hi = corner.max(dim=1, keepdim=True).values
     scale = float(2 ** 20 - 1)
     q = ((corner - lo) / torch.clamp(hi - lo, min=1e-300) * scale).clamp(0, scale).to(i64)
-    order = torch.arange(nel, device=dev, dtype=i64)
+    if order is None:
+        order = torch.arange(nel, device=dev, dtype=i64)
+        seg_cnt = torch.tensor([nel], device=dev, dtype=i64)
     pos = torch.arange(nel, device=dev, dtype=i64)
-    seg_cnt = torch.tensor([nel], device=dev, dtype=i64)
-    seg_k = torch.tensor([(nel + T - 1) // T], device=dev, dtype=i64)
+    seg_k = (seg_cnt + T - 1) // T
     while int(seg_k.max()) > 1:
         nseg = int(seg_cnt.shape[0])
         seg_of = torch.repeat_interleave(torch.arange(nseg, device=dev, dtype=i64), seg_cnt)

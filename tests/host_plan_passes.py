@@ -118,6 +118,26 @@ def apply(fp, T, spread=True, renumber=True):
     return fp
 
 
+def apply2(fp, T, spread=True, renumber=True):
+    """Same passes on a second-generation plan (skfem_b200/fused2.py) built with
+    ``defer_finalize=True``: bank spreading works on the column-major ELL array ``fp._ell``,
+    vertex renumbering on the records (whose header keeps nverts / off_verts in place)."""
+    lib = C.CDLL(build())
+    if spread and fp._ids_base16 is not None:
+        ell = fp._ell.numpy()
+        pos = np.ascontiguousarray(fp._gcum.numpy()[:-1].astype(np.int64))
+        length = np.ascontiguousarray(fp._grp_len.numpy().astype(np.int32))
+        lib.host_plan_spread(C.c_void_p(ell.ctypes.data), C.c_void_p(pos.ctypes.data),
+                             C.c_void_p(length.ctypes.data), C.c_int64(len(pos)),
+                             C.c_int(10 * T))
+    if renumber:
+        rec = fp.rec.numpy()
+        rs = np.ascontiguousarray(fp.rec_start.numpy().astype(np.uint64))
+        lib.host_plan_renumber(C.c_void_p(rec.ctypes.data), C.c_void_p(rs.ctypes.data),
+                               C.c_int(fp.ntiles), C.c_int(T))
+    return fp
+
+
 def combine(fp, scratch, csr):
     """p1_combine_kernel (csrc/skb_p1_fused.cu) on the host: adds the per-tile partials in
     ``scratch`` into ``csr`` (both float64 numpy arrays) following the plan's sptr / gslot."""

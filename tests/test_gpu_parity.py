@@ -224,7 +224,8 @@ def test_fused_p1_path(tile, threads, ring):
     reference, bit-identical between repeated runs."""
     from skfem_b200.models.poisson import laplace
     from skfem_b200 import form as F
-    F.set_options(fused=True, fused_tile=tile, fused_threads=threads, fused_ring=ring)
+    F.set_options(fused=True, fused_version=1, fused_tile=tile, fused_threads=threads,
+                  fused_ring=ring)
     try:
         for name in ["tet_p1_tensor6", "tet_p1_ball2", "tet_p1_refined3", "tet_p1_morphed5",
                      "tet_p1_tensor_nonuniform"]:
@@ -275,7 +276,8 @@ def test_fused_p1_path(tile, threads, ring):
         np.testing.assert_allclose(As.data, Aso.data, rtol=RTOL,
                                    atol=RTOL * np.abs(Aso.data).max())
     finally:
-        F.set_options(fused=True, fused_tile=512, fused_threads=480, fused_ring=4)
+        F.set_options(fused=True, fused_version=2, fused_tile=512, fused_threads=480,
+                      fused_ring=4)
 
 
 def test_baseline_config2_full_size_properties():
@@ -355,12 +357,12 @@ def test_fused_fast_arithmetic_within_tolerance():
     ref = O.assemble_bilinear(O.laplace, O.cell_basis(om, O.element("tet_p1")))
     b = fem.Basis(m, fem.ElementTetP1())
     try:
-        set_options(fused_arith="fast")
+        set_options(fused_arith="fast", fused_version=1)
         laplace.assemble(b)                       # cold (always exact: builds the plan)
         A1 = laplace.assemble(b)                  # warm: fused kernel, fast arithmetic
         A2 = laplace.assemble(b)
     finally:
-        set_options(fused_arith="exact")
+        set_options(fused_arith="exact", fused_version=2)
     A3 = laplace.assemble(b)                      # warm, exact arithmetic
     assert np.array_equal(A1.indptr, ref.indptr) and np.array_equal(A1.indices, ref.indices)
     assert np.array_equal(A1.data, A2.data)
@@ -386,7 +388,7 @@ def test_fused_kd_tiling_parity():
     q[1] = q[1] + 0.02 * q[2] ** 2
     cases.append(fem.MeshTet(q, cases[0].t))
     try:
-        set_options(fused_tiling="kd")
+        set_options(fused_tiling="kd", fused_version=1)
         for m in cases:
             om = mesh_of(dict(p=m.p, t=m.t), "tet")
             ref = O.assemble_bilinear(O.laplace, O.cell_basis(om, O.element("tet_p1")))
@@ -400,4 +402,4 @@ def test_fused_kd_tiling_parity():
             scale = np.abs(ref.data).max()
             np.testing.assert_allclose(A1.data, ref.data, rtol=1e-12, atol=1e-12 * scale)
     finally:
-        set_options(fused_tiling="morton")
+        set_options(fused_tiling="morton", fused_version=2)
