@@ -176,13 +176,14 @@ int skb_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *
 
 /* ---- fused P1 path, second generation (csrc/skb_p1_fused2.cu, plan: skfem_b200/fused2.py) ----
  * Same replacement as above.  Elements are ordered by a k-d tree into super-tiles (compact
- * boxes of whole tiles, st_tile0[s] = first tile of super-tile s); a CTA (tile_elems threads,
- * one element each, several CTAs per SM) walks whole super-tiles: per tile P1 (local matrices
+ * boxes of tiles_per_super consecutive tiles, the last one possibly shorter); a CTA (tile_elems
+ * compute threads, one element each, + one producer warp; several CTAs per SM) walks whole
+ * super-tiles: per tile P1 (local matrices
  * in registers -> shared memory) and P2 (fixed-order per-slot sums) accumulate into a pool of
  * pool_cap accumulators in shared memory, one per canonical CSR slot of the super-tile; after
  * the last tile the pool is flushed in CSR order through the flush table fl (uint32 pairs
- * {CSR slot, or bit31 | scratch position; mirror slot or 0xFFFFFFFF}, st_fl0[s] = first entry
- * of super-tile s).  Only slots shared between super-tiles go through scratch + skb_p1_combine2.
+ * {CSR slot, or bit31 | scratch position, or 0xFFFFFFFF for a padding entry; mirror slot or
+ * 0xFFFFFFFF}, st_fl0[s] = first entry of super-tile s, always even; fetched by TMA).  Only slots shared between super-tiles go through scratch + skb_p1_combine2.
  * mode: 0 any coordinates / any equal-weight rule (IEEE division), 1 nqp == 4 and coordinates
  * 0 or within [2^-60, 2^60] (shared reciprocal + Markstein corrections == IEEE division),
  * 2 additionally coordinates within [2^-28, 2^28] and w within [2^-20, 1] (the quadrature sum
@@ -198,8 +199,8 @@ int skb_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *
 int64_t skb_p1_fused2_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap,
                                  int32_t vcap, int32_t pool_cap);
 int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
-                             const uint64_t *rec_start, const int32_t *st_tile0,
-                             const int64_t *st_fl0, const void *fl, int32_t nst,
+                             const uint64_t *rec_start, const int64_t *st_fl0, const void *fl,
+                             int32_t nst, int32_t ntiles, int32_t tiles_per_super,
                              int32_t tile_elems, int32_t ring, int32_t rec_cap, int32_t vcap,
                              int32_t pool_cap, int32_t ctas_per_sm, int32_t mode, double w,
                              int32_t nqp, double *csr_data, double *scratch, int32_t *flag,

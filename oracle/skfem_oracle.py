@@ -700,6 +700,34 @@ def inv(A):                                     # helpers.py:179-207
     return out
 
 
+def curl(u):                                    # helpers.py:39-57
+    g = u.grad
+    if g.ndim == 3 and g.shape[0] == 2:
+        return np.array([g[1], -g[0]])
+    if g.ndim == 4 and g.shape[0] == 2:
+        return g[1, 0] - g[0, 1]
+    return np.array([g[2, 1] - g[1, 2], g[0, 2] - g[2, 0], g[1, 0] - g[0, 1]])
+
+
+def cross(A, B):                                # helpers.py:210-218
+    if A.shape[0] == 2:
+        return A[0] * B[1] - A[1] * B[0]
+    return np.array([A[1] * B[2] - A[2] * B[1], A[2] * B[0] - A[0] * B[2],
+                     A[0] * B[1] - A[1] * B[0]])
+
+
+def curluv(u, v, _):                            # models/general.py:15-17
+    return dot(curl(u), v)
+
+
+def rot(v, w):                                  # models/general.py:20-22
+    return dot(curl(v), w['w'])
+
+
+def vrot(v, w):                                 # models/general.py:25-27
+    return dot(v, curl(w['w']))
+
+
 def divu(u, v, _):                              # models/general.py:7-9
     return div(u) * v
 

@@ -42,10 +42,9 @@ struct P1v2Args {
   int64_t npts;
   const unsigned char *rec;     // concatenated tile records
   const uint64_t *rec_start;    // [ntiles+1] byte offsets (multiples of 16)
-  const int32_t *st_tile0;      // [nst+1] first tile of every super-tile
-  const int64_t *st_fl0;        // [nst+1] first flush entry of every super-tile
+  const int64_t *st_fl0;        // [nst+1] first flush entry of every super-tile (even)
   const uint2 *fl;              // flush table: {target, mirror target}
-  int32_t nst;
+  int32_t nst, ntiles, S;       // super-tiles, tiles, tiles per super-tile
   int32_t rec_cap;              // largest record, bytes (multiple of 16)
   int32_t vcap;                 // most vertices in one tile (even)
   int32_t pool_cap;             // most accumulators in one super-tile (even)
@@ -93,7 +92,7 @@ __device__ __forceinline__ void mbar_wait2(uint64_t *bar, unsigned parity) {
   }
 }
 // TMA bulk copy global -> shared, completion counted on an mbarrier; evict-first in L2 (the
-// records are read once per step)
+// records and flush tables are read once per step)
 __device__ __forceinline__ void tma_bulk_g2s2(void *dst, const void *src, unsigned bytes,
                                               uint64_t *bar) {
   uint64_t policy;
@@ -104,116 +103,157 @@ __device__ __forceinline__ void tma_bulk_g2s2(void *dst, const void *src, unsign
       ::"r"(smem_u32_2(dst)), "l"(src), "r"(bytes), "r"(smem_u32_2(bar)), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void cp_async8_2(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32_2(dst)), "l"(src)
-               : "memory");
+__device__ __forceinline__ void cp_async8_2(uint32_t dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
 }
 
 __device__ __forceinline__ unsigned nonzero_bits(double v) {   // v != +-0, integer pipe only
-  return (((unsigned)__double2hiint(v) << 1) | (unsigned)__double2loint(v)) != 0u;
+  return (((unsigned)__double2hiint(v) & 0x7fffffffu) | (unsigned)__double2loint(v)) != 0u;
 }
-
-// walks the tiles of the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-struct TileCursor {
-  int st, tile, end;
-};
 
 // MODE 0: any mesh, any equal-weight rule: IEEE division, numpy's quadrature sum evaluated
 //         term by term.
-// MODE 1: nqp == 4, coordinates within the exact_div-safe range (P1FusedPlan.tame >= 1): one
-//         reciprocal + Markstein corrections per quotient (skb_common.cuh exact_div).
+// MODE 1: nqp == 4, coordinates within the exact_div-safe range: one reciprocal + Markstein
+//         corrections per quotient (skb_common.cuh exact_div).
 // MODE 2: additionally coordinates within [2^-28, 2^28] and the weight within [2^-20, 1]: then
 //         d * dx is a normal number or exactly 0 for every entry, so numpy's
 //         ((v + v) + v) + v  (v = d * dx) equals 4 v = d * (4 dx) bit for bit - one
 //         multiplication instead of three operations (proof in DESIGN.md).
 // MODE 3: opt-in fast arithmetic (FMA + one reciprocal; values within a few ulp per term).
+//
+// Roles: threads [0, T) compute (one element each in P1, the tile's slot groups in P2, the
+// flush), one more warp whose lane 0 is the producer: it waits for records / flush tables and
+// issues the TMA copies, so the latency of its global loads never delays a compute warp.
+// The CTA processes the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ...; its j-th tile
+// uses record buffer j % NR.
 template <int T, int MODE>
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T + 32, T >= 512 ? 2 : (T >= 256 ? 3 : 6))
 p1tet_laplace_fused2_kernel(const P1v2Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int VSTRIDE = 10 * T + 16;   // + one staged 0.0 per bank pair
-  double *vals = reinterpret_cast<double *>(smem_raw);             // [VSTRIDE]
-  double *coords = vals + VSTRIDE;                                 // [3][vcap]
-  double *pool = coords + 3 * (size_t)a.vcap;                      // [pool_cap]
-  unsigned char *recs = reinterpret_cast<unsigned char *>(pool + a.pool_cap);
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(recs + (size_t)a.ring * a.rec_cap);
+  constexpr int NVALS = 10 * T + 16;     // + one staged 0.0 per bank pair
+  double *vals = reinterpret_cast<double *>(smem_raw);             // [NVALS]
+  double *coords = vals + NVALS;                                   // [2][vcap][3] (AoS)
+  double *pool = coords + 6 * (size_t)a.vcap;                      // [pool_cap]
+  uint2 *flbuf = reinterpret_cast<uint2 *>(pool + a.pool_cap);     // [pool_cap] flush table
+  unsigned char *recs = reinterpret_cast<unsigned char *>(flbuf + a.pool_cap);
+  const int NR = a.ring;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(recs + (size_t)NR * a.rec_cap);   // [NR + 1]
+  int *fl_np = reinterpret_cast<int *>(mbar + NR + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = T / 32;
-  const int NR = a.ring;
+  const bool is_compute = tid < T;
+  const bool is_producer = tid == T;
+  const int S = a.S, G = (int)gridDim.x;
 
-  auto start = [&](TileCursor &c, int st) {
-    c.st = st;
-    if (st < a.nst) { c.tile = a.st_tile0[st]; c.end = a.st_tile0[st + 1]; }
-    else { c.tile = -1; c.end = -1; }
+  // this CTA's tile sequence
+  int st = (int)blockIdx.x;
+  if (st >= a.nst) return;
+  const int nst_mine = (a.nst - st + G - 1) / G;
+  const bool owns_last = ((a.nst - 1 - st) % G) == 0;
+  const int nmine = nst_mine * S - (owns_last ? a.nst * S - a.ntiles : 0);
+  int tile = st * S, tend = min(tile + S, a.ntiles);
+
+  // producer state: issue cursor, wait cursor
+  int p_st = st, p_tile = tile, p_tend = tend, p_slot = 0, p_issued = 0;
+  int w_slot = 2 % NR;
+  unsigned w_par = 0, fl_par = 0;
+  auto issue_record = [&]() {         // producer: fetch the record of the next tile in sequence
+    if (p_issued < nmine) {
+      const uint64_t b0 = a.rec_start[p_tile];
+      const unsigned bytes = (unsigned)(a.rec_start[p_tile + 1] - b0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx2(&mbar[p_slot], bytes);
+      tma_bulk_g2s2(recs + (size_t)p_slot * a.rec_cap, a.rec + b0, bytes, &mbar[p_slot]);
+      if (++p_tile >= p_tend) {
+        p_st += G;
+        p_tile = p_st * S;
+        p_tend = min(p_tile + S, a.ntiles);
+      }
+    }
+    ++p_issued;
+    if (++p_slot == NR) p_slot = 0;
   };
-  auto advance = [&](TileCursor &c) {
-    if (c.tile < 0) return;
-    if (++c.tile >= c.end) start(c, c.st + (int)gridDim.x);
+  auto issue_flush_table = [&](int s) {   // producer: fetch the flush table of super-tile s
+    const int64_t f0 = a.st_fl0[s];
+    const int np = (int)(a.st_fl0[s + 1] - f0);          // even
+    *fl_np = np;
+    if (np > 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx2(&mbar[NR], (unsigned)np * 8u);
+      tma_bulk_g2s2(flbuf, a.fl + f0, (unsigned)np * 8u, &mbar[NR]);
+    }
   };
-  auto rec_of = [&](int it) { return recs + (size_t)(it % NR) * a.rec_cap; };
-  auto issue = [&](int it, const TileCursor &c) {     // one thread: fetch the record of c.tile
-    if (c.tile < 0) return;
-    const uint64_t b0 = a.rec_start[c.tile];
-    const unsigned bytes = (unsigned)(a.rec_start[c.tile + 1] - b0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx2(&mbar[it % NR], bytes);
-    tma_bulk_g2s2(rec_of(it), a.rec + b0, bytes, &mbar[it % NR]);
-  };
-  auto wait_rec = [&](int it) { mbar_wait2(&mbar[it % NR], (unsigned)((it / NR) & 1)); };
-  auto gather = [&](int it) {   // async gather of the vertex coordinates of the tile in slot it
-    const unsigned char *r = rec_of(it);
+  auto gather = [&](const unsigned char *r, int par) {   // async gather of a tile's vertices
     const RecHeader2 *h = reinterpret_cast<const RecHeader2 *>(r);
     const int nv = (int)h->nverts;
     const int32_t *verts = reinterpret_cast<const int32_t *>(r + h->off_verts);
-    double *dx = coords, *dy = dx + a.vcap, *dz = dy + a.vcap;
+    const uint32_t dst = smem_u32_2(coords + (size_t)par * 3 * a.vcap);
     const double *px = a.p, *py = a.p + a.npts, *pz = a.p + 2 * a.npts;
+#pragma unroll 1
     for (int i = tid; i < nv; i += T) {
       const int32_t gv = verts[i];
-      cp_async8_2(dx + i, px + gv);
-      cp_async8_2(dy + i, py + gv);
-      cp_async8_2(dz + i, pz + gv);
+      cp_async8_2(dst + 24 * i, px + gv);
+      cp_async8_2(dst + 24 * i + 8, py + gv);
+      cp_async8_2(dst + 24 * i + 16, pz + gv);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   if (tid == 0) {
-    for (int i = 0; i < NR; ++i) mbar_init2(&mbar[i], 1);
+    for (int i = 0; i <= NR; ++i) mbar_init2(&mbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = 0; i < 16; ++i) vals[10 * T + i] = 0.0;
   }
   __syncthreads();
-  TileCursor cur, pre;
-  start(cur, (int)blockIdx.x);
-  if (cur.tile < 0) return;
-  pre = cur;
-  int it_pre = 0;
-  if (tid == 0) {                       // prologue: NR records in flight
-    for (; it_pre < NR; ++it_pre) { issue(it_pre, pre); advance(pre); }
+  if (is_producer) {                    // prologue: NR records and the first flush table in flight
+    for (int i = 0; i < NR; ++i) issue_record();
+    issue_flush_table(st);
   }
-  wait_rec(0);
-  gather(0);
+  mbar_wait2(&mbar[0], 0);
+  if (nmine > 1) mbar_wait2(&mbar[1], 0);
+  if (is_compute) gather(recs, 0);
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   const double w1 = a.w;
   const double w4 = a.w * 4.0;
+  const uint32_t vals_s = smem_u32_2(vals);
+  const uint32_t pool_s = smem_u32_2(pool);
   unsigned bad = 0;
-  for (int it = 0; cur.tile >= 0; ++it) {
-    const unsigned char *r = rec_of(it);
+  int slot = 0, par = 0;
+  bool first_of_st = false;             // the first super-tile's flush table is already in flight
+  // Invariant at the top of iteration `it`: the records of this tile and of the next one have
+  // landed and are visible to every thread; coords[par] holds this tile's vertices.
+#pragma unroll 1
+  for (int it = 0; it < nmine; ++it) {
+    const int slot1 = slot + 1 == NR ? 0 : slot + 1;
+    const unsigned char *r = recs + (size_t)slot * a.rec_cap;
     const RecHeader2 *h = reinterpret_cast<const RecHeader2 *>(r);
+    const bool has_next = it + 1 < nmine;
+    const bool last_of_st = tile + 1 >= tend;
+    // the next tile's vertex coordinates travel while this tile is computed and reduced
+    if (is_compute && has_next) gather(recs + (size_t)slot1 * a.rec_cap, par ^ 1);
     // ---- P1: local matrix of element `tid` -> vals -------------------------------------
-    if (!(a.debug & 1)) {
+    if (is_compute && !(a.debug & 1)) {
       const ushort4 v = reinterpret_cast<const ushort4 *>(r + sizeof(RecHeader2))[tid];
       if (v.x != 0xFFFF) {   // not a padding element of a short tile
-        const int i0 = v.x & 0x3ff, i1 = v.y & 0x3ff, i2 = v.z & 0x3ff, i3 = v.w & 0x3ff;
         const unsigned keep = (unsigned)(v.x >> 10) | ((unsigned)(v.y >> 10) << 6);
-        const double *sx = coords, *sy = sx + a.vcap, *sz = sy + a.vcap;
+        const uint32_t cb = smem_u32_2(coords + (size_t)par * 3 * a.vcap);
+        const uint32_t c0 = cb + 24u * (v.x & 0x3ffu), c1 = cb + 24u * (v.y & 0x3ffu),
+                       c2 = cb + 24u * (v.z & 0x3ffu), c3 = cb + 24u * (v.w & 0x3ffu);
         double A[3][3];
         {
-          const double x0 = sx[i0], y0 = sy[i0], z0 = sz[i0];
-          A[0][0] = sx[i1] - x0; A[0][1] = sx[i2] - x0; A[0][2] = sx[i3] - x0;
-          A[1][0] = sy[i1] - y0; A[1][1] = sy[i2] - y0; A[1][2] = sy[i3] - y0;
-          A[2][0] = sz[i1] - z0; A[2][1] = sz[i2] - z0; A[2][2] = sz[i3] - z0;
+          const double x0 = lds_f64(c0), y0 = lds_f64(c0 + 8), z0 = lds_f64(c0 + 16);
+          A[0][0] = lds_f64(c1) - x0; A[0][1] = lds_f64(c2) - x0; A[0][2] = lds_f64(c3) - x0;
+          A[1][0] = lds_f64(c1 + 8) - y0; A[1][1] = lds_f64(c2 + 8) - y0;
+          A[1][2] = lds_f64(c3 + 8) - y0;
+          A[2][0] = lds_f64(c1 + 16) - z0; A[2][1] = lds_f64(c2 + 16) - z0;
+          A[2][2] = lds_f64(c3 + 16) - z0;
         }
         double det, n[3][3], inv[3][3];
         if (MODE == 3) {
@@ -276,6 +316,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
         const double dx = adet * w1;            // cell_basis.py:104-105
         const double dx4 = adet * w4;           // == 4 * dx exactly (power-of-two scaling)
         unsigned nz = 0;
+        const uint32_t out_s = vals_s + 8u * tid;
         int k = 0;
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp)
@@ -300,62 +341,70 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
               }
             }
             nz |= nonzero_bits(val) << k;
-            vals[k * T + tid] = val;
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(out_s + 8u * (unsigned)(k * T)), "d"(val)
+                         : "memory");
           }
         bad |= (nz ^ keep);
-        if (a.nz_out) a.nz_out[(size_t)cur.tile * T + tid] = (uint16_t)nz;
+        if (a.nz_out) a.nz_out[(size_t)tile * T + tid] = (uint16_t)nz;
       }
     }
-    // the record of the next tile has been in flight for at least NR - 1 iterations
-    TileCursor nxt = cur;
-    advance(nxt);
-    if (tid == 0 && nxt.tile >= 0) wait_rec(it + 1);
-    __syncthreads();   // (A) vals complete; record it+1 visible to everybody; coords free
-    if (nxt.tile >= 0) gather(it + 1);
+    __syncthreads();   // (A) vals complete
+    if (is_producer) {
+      // the record two tiles ahead must be visible at the top of the next iteration (its
+      // vertex list feeds the gather); it has been in flight for NR - 2 iterations
+      if (it + 2 < nmine) mbar_wait2(&mbar[w_slot], w_par);
+      if (++w_slot == NR) { w_slot = 0; w_par ^= 1u; }
+      // every compute thread has left the previous super-tile's flush: its table buffer is free
+      if (first_of_st) issue_flush_table(st);
+      if (last_of_st && *fl_np > 0) { mbar_wait2(&mbar[NR], fl_par); fl_par ^= 1u; }
+    }
     // ---- P2: per-slot sums in fixed order (sliced ELL), accumulated into the pool ---------
-    if (!(a.debug & 2)) {
+    if (is_compute && !(a.debug & 2)) {
       const int ngroups = (int)h->ngroups;
       const uint32_t *grp = reinterpret_cast<const uint32_t *>(r + h->off_grp);
-      const uint16_t *lanew = reinterpret_cast<const uint16_t *>(r + h->off_lane);
-      const uint32_t *ids = reinterpret_cast<const uint32_t *>(r + h->off_ids);
+      const uint16_t *lanew = reinterpret_cast<const uint16_t *>(r + h->off_lane) + lane;
+      const uint32_t *ids = reinterpret_cast<const uint32_t *>(r + h->off_ids) + lane;
 #pragma unroll 1
       for (int gi = warp; gi < ngroups; gi += NW) {
         const uint32_t gw = grp[gi];
-        const int rows = (int)(gw >> 16);                  // two ELL columns per row
-        const uint32_t *cb = ids + (size_t)(gw & 0xffffu) * 32 + lane;
-        const unsigned lw = lanew[gi * 32 + lane];
-        double acc = 0.0;
+        const int rows = (int)((gw >> 16) & 0x7fffu);      // two ELL columns per row
+        const uint32_t *cb = ids + (size_t)(gw & 0xffffu) * 32;
+        const unsigned lw = lanew[gi * 32];
+        // the words hold byte offsets into vals; even and odd columns are summed separately
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll 2
         for (int c = 0; c < rows; ++c) {
           const uint32_t w2 = cb[c * 32];
-          const double a0 = vals[w2 & 0xffffu], a1 = vals[w2 >> 16];
-          acc = acc + a0;
-          acc = acc + a1;
+          s0 = s0 + lds_f64(vals_s + (w2 & 0xffffu));
+          s1 = s1 + lds_f64(vals_s + (w2 >> 16));
         }
-        // long lists are split over 2 or 4 adjacent lanes: fixed combination tree
-        // (l + l+1) + (l+2 + l+3), selected by the leader lane
-        const double t1 = acc + __shfl_down_sync(0xffffffffu, acc, 1);
-        const double t2 = t1 + __shfl_down_sync(0xffffffffu, t1, 2);
-        if (lw != 0xFFFFu) {
+        double acc = s0 + s1;
+        if (gw & 0x80000000u) {
+          // long lists are split over 2 or 4 adjacent lanes: fixed combination tree
+          // (l + l+1) + (l+2 + l+3), selected by the leader lane
+          const double t1 = acc + __shfl_down_sync(0xffffffffu, acc, 1);
+          const double t2 = t1 + __shfl_down_sync(0xffffffffu, t1, 2);
           const unsigned fs = (lw >> 13) & 3u;
           acc = fs == 0 ? acc : (fs == 1 ? t1 : t2);
-          const unsigned pi = lw & 0x1fffu;
-          if (lw & 0x8000u) pool[pi] = acc;                // first tile of the super-tile touching it
-          else pool[pi] = pool[pi] + acc;
+        }
+        if (lw != 0xFFFFu) {
+          const uint32_t pa = pool_s + ((lw & 0x1fffu) << 3);
+          if (!(lw & 0x8000u)) acc = lds_f64(pa) + acc;    // not the first tile touching it
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(pa), "d"(acc) : "memory");
         }
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();   // (B) vals, record `it` free; coords of the next tile visible; pool updated
-    if (tid == 0) { issue(it_pre, pre); advance(pre); ++it_pre; }
+    __syncthreads();   // (B) vals, record `slot` free; coords of the next tile visible; pool updated
+    if (is_producer) issue_record();
     // ---- flush: the super-tile's pool -> csr_data / scratch, in CSR order --------------------
-    if (nxt.st != cur.st) {
-      const int64_t f0 = a.st_fl0[cur.st];
-      const int np = (int)(a.st_fl0[cur.st + 1] - f0);
-      if (!(a.debug & 64)) {
-        for (int i = tid; i < np; i += T) {
-          const uint2 m = __ldcs(a.fl + f0 + i);
-          const double val = pool[i];
+    if (last_of_st && is_compute && !(a.debug & 64)) {
+      const int np = *fl_np;
+#pragma unroll 2
+      for (int i = tid; i < np; i += T) {
+        const uint2 m = flbuf[i];
+        const double val = pool[i];
+        if (m.x != 0xffffffffu) {
           if (m.x & 0x80000000u) a.scratch[m.x & 0x7fffffffu] = val;
           else a.csr_data[m.x] = val;
           if (m.y != 0xffffffffu) a.csr_data[m.y] = val;
@@ -363,7 +412,17 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
       }
       // the next super-tile's first pool write comes after barrier (A) of its first tile
     }
-    cur = nxt;
+    // next tile of the sequence
+    first_of_st = last_of_st;
+    if (last_of_st) {
+      st += G;
+      tile = st * S;
+      tend = min(tile + S, a.ntiles);
+    } else {
+      ++tile;
+    }
+    slot = slot1;
+    par ^= 1;
   }
   if (bad & 0x3ffu) atomicOr(a.flag, 1);
 }
@@ -389,14 +448,14 @@ static int launch_fused2(const P1v2Args &a, size_t smem, int sms, int ctas_per_s
   auto k = p1tet_laplace_fused2_kernel<T, MODE>;
   SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  SKB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T, smem));
+  SKB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T + 32, smem));
   if (occ < 1) return SKB_ETOOBIG;
   if (ctas_per_sm > 0 && occ > ctas_per_sm) occ = ctas_per_sm;
   int free_sms = sm_reserve();
   if (free_sms > sms - 1) free_sms = sms - 1;
   const int cap = occ * (sms - free_sms);
   const int grid = a.nst < cap ? a.nst : cap;
-  k<<<grid, T, smem, st>>>(a);
+  k<<<grid, T + 32, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -404,9 +463,9 @@ static int launch_fused2(const P1v2Args &a, size_t smem, int sms, int ctas_per_s
 
 extern "C" int64_t skb_p1_fused2_smem_bytes(int32_t tile_elems, int32_t ring, int32_t rec_cap,
                                             int32_t vcap, int32_t pool_cap) {
-  return (int64_t)(sizeof(double) * ((10 * (size_t)tile_elems + 16) + 3 * (size_t)vcap +
-                                     (size_t)pool_cap) +
-                   (size_t)ring * rec_cap + 8 * (size_t)ring + 32);
+  return (int64_t)(sizeof(double) * ((10 * (size_t)tile_elems + 16) + 6 * (size_t)vcap +
+                                     2 * (size_t)pool_cap) +
+                   (size_t)ring * rec_cap + 8 * ((size_t)ring + 1) + 32);
 }
 
 // Warm fused P1-tet Laplace assembly (see the top of this file).  mode: 0 generic, 1 exact
@@ -417,22 +476,25 @@ extern "C" int64_t skb_p1_fused2_smem_bytes(int32_t tile_elems, int32_t ring, in
 // nz_out != NULL (plan time): only the local matrices are formed and the 10-bit zero mask of
 // element e of tile t is stored at nz_out[t * tile_elems + e]; nothing else is written.
 extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
-                                        const uint64_t *rec_start, const int32_t *st_tile0,
-                                        const int64_t *st_fl0, const void *fl, int32_t nst,
-                                        int32_t tile_elems, int32_t ring, int32_t rec_cap,
+                                        const uint64_t *rec_start, const int64_t *st_fl0,
+                                        const void *fl, int32_t nst, int32_t ntiles,
+                                        int32_t tiles_per_super, int32_t tile_elems,
+                                        int32_t ring, int32_t rec_cap,
                                         int32_t vcap, int32_t pool_cap, int32_t ctas_per_sm,
                                         int32_t mode, double w, int32_t nqp, double *csr_data,
                                         double *scratch, int32_t *flag, uint16_t *nz_out,
                                         void *stream) {
   using namespace skb;
   if (nst < 0 || !p || nqp <= 0 || vcap <= 0 || (vcap & 1) || pool_cap <= 0 || (pool_cap & 1) ||
-      rec_cap <= 0 || (rec_cap & 15) || ring < 2 || ring > 8 || !flag)
+      rec_cap <= 0 || (rec_cap & 15) || ring < 3 || ring > 8 || !flag || tiles_per_super < 1 ||
+      ntiles > (int64_t)nst * tiles_per_super || ntiles <= (int64_t)(nst - 1) * tiles_per_super)
     return SKB_EINVAL;
   if (mode < 0 || mode > 3 || ((mode == 1 || mode == 2) && nqp != 4)) return SKB_EINVAL;
   if (nst == 0) return SKB_OK;
   P1v2Args a;
   a.p = p; a.npts = npts; a.rec = (const unsigned char *)rec; a.rec_start = rec_start;
-  a.st_tile0 = st_tile0; a.st_fl0 = st_fl0; a.fl = (const uint2 *)fl; a.nst = nst;
+  a.st_fl0 = st_fl0; a.fl = (const uint2 *)fl; a.nst = nst; a.ntiles = ntiles;
+  a.S = tiles_per_super;
   a.rec_cap = rec_cap; a.vcap = vcap; a.pool_cap = pool_cap; a.ring = ring;
   a.csr_data = csr_data; a.scratch = scratch; a.w = w; a.nqp = nqp;
   a.debug = debug_flags(); a.flag = flag; a.nz_out = nz_out;

@@ -267,7 +267,8 @@ class CellBasis(AbstractBasis):
         if hasattr(self, "_doflocs"):
             del self._doflocs
         from . import fused2
-        keep = {}
+        # value-independent (LinearForm scatter) and mask-validated plans stay valid
+        keep = {k: v for k, v in self._plans.items() if k in ("linear", "by-mask")}
         for k, fp in self._plans.items():
             if isinstance(k, tuple) and k and k[0] == "fused" and getattr(fp, "version", 1) == 2:
                 fp.mode = fused2.arithmetic_mode(d["p"], fp.w, fp.nqp)

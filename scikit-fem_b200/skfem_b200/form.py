@@ -167,6 +167,40 @@ def _stream():
     return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
 
 
+_TOKENS = iter(range(1, 1 << 62))
+
+
+def _basis_token(basis):
+    """Process-unique integer of a basis object (never reused, unlike ``id``)."""
+    tok = getattr(basis, "_token", None)
+    if tok is None:
+        tok = basis._token = next(_TOKENS)
+    return tok
+
+
+MASK_PLANS_KEPT = 4
+
+
+def _mask_plan_get(ubasis, vbasis, nz):
+    """Plan of a traced form whose local data has exactly the zero mask ``nz`` (bool device
+    tensor (Nbu, Nbv, nel)) on this pair of bases, or None.  The plan (indptr / indices /
+    entry -> slot permutation, coo_data.py:34-36) depends on the form only through that mask,
+    so forms are interchangeable here and a form whose coefficients changed is re-planned
+    exactly when its pattern did."""
+    torch = _torch()
+    tok = _basis_token(vbasis)
+    for ent in ubasis._plans.get("by-mask", ()):
+        if ent[0] == tok and ent[1].shape == nz.shape and bool(torch.equal(ent[1], nz)):
+            return ent[2]
+    return None
+
+
+def _mask_plan_put(ubasis, vbasis, nz, plan):
+    lst = ubasis._plans.setdefault("by-mask", [])
+    lst.append((_basis_token(vbasis), nz, plan))
+    del lst[:-MASK_PLANS_KEPT]
+
+
 def build_plan(dofs_v, dofs_u, nel, shape, local, drop_zeros=True):
     """Sort/unique on the device (skb_plan_symbolic + skb_plan_finalize)."""
     torch = _torch()
@@ -435,10 +469,13 @@ class BilinearForm(Form):
         return out
 
     def _plan_key(self, ubasis, vbasis, kwargs):
-        if kwargs:
+        """Cache key of the sparsity plan - only for library forms without parameters: their
+        local data, hence the value-dependent pattern, is a function of the basis alone.
+        Traced forms (closures, ``w`` fields, ``partial`` copies) get no key: their plans
+        are cached by *zero mask* (``_mask_plan``)."""
+        if kwargs or self.native is None:
             return None
-        return (id(self.form) if self.native is None else self.native[:3],
-                id(vbasis) if vbasis is not None else None)
+        return (self.native[:3], _basis_token(vbasis) if vbasis is not None else None)
 
     def assemble_device(self, ubasis, vbasis=None, out=None, slot_map=None,
                         **kwargs) -> DeviceCSR:
@@ -509,6 +546,12 @@ class BilinearForm(Form):
                                   l2_persist=bool(_CONFIG["fused_l2_persist"]))
                     return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
         local = self._local(ubasis, vbasis, **kwargs)
+        nz = None
+        if plan is None and key is None:
+            # traced form: the pattern is a function of (element_dofs, zero mask of the
+            # local data) only - reuse a cached plan iff the mask is identical
+            nz = local != 0
+            plan = _mask_plan_get(ubasis, vb, nz)
         if plan is None:
             if out is not None:
                 raise ValueError("out= needs an existing plan: assemble once without it")
@@ -516,6 +559,8 @@ class BilinearForm(Form):
                               (vb.N, ubasis.N), local, drop_zeros=True)
             if key is not None:
                 ubasis._plans[key] = plan
+            else:
+                _mask_plan_put(ubasis, vb, nz, plan)
         data = out if (out is not None and slot_map is None) else torch.empty(
             plan.nnz, dtype=torch.float64, device=local.device)
         code = _lib.lib().skb_csr_reduce(local.data_ptr(), plan.perm.data_ptr(),

@@ -18,12 +18,14 @@ record (one TMA bulk copy in the kernel):
             *kept mask*: bit k set <=> local entry k (row-major upper triangle) is nonzero
             in the cold assembly that defined the CSR pattern
     verts   nverts int32  global vertex ids of the tile
-    grp     per group of 32 lanes: uint32 (offset / 32 words into ids) | rows << 16
+    grp     per group of 32 lanes: uint32 (offset / 32 words into ids) | rows << 16 |
+            (group contains split lists) << 31
     lane    per lane uint16: pool index (13 bits) | fsel << 13 | first-touch << 15;
             0xFFFF for lanes that own no slot (members of a split list, padding)
-    ids     sliced-ELL staging indices k(a,b)*T + e_local, two per uint32: row r of lane l
-            of a group at base + 32 r + l holds columns 2r (low half) and 2r + 1; short
-            lists are padded with 10*T + b, the index of a staged 0.0
+    ids     sliced-ELL staging positions 8 * (k(a,b)*T + e_local) (byte offsets), two per
+            uint32: row r of lane l of a group at base + 32 r + l holds columns 2r (low half)
+            and 2r + 1; short lists are padded with 8 * (10*T + b), the offset of a staged 0.0;
+            a lane's sum is (sum of its even columns) + (sum of its odd columns)
 
 A *tile slot* is a canonical (row <= col) CSR slot touched by the tile; the Laplace local
 matrix is bitwise symmetric, so the mirror slot gets the same sum.  Every super-tile owns
@@ -187,12 +189,16 @@ def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, t
     pu_st = pu // nnz
     pu_gslot = pu - pu_st * nnz
     st_ids = arange(nst + 1)
-    st_fl0 = torch.searchsorted(pu_st, st_ids)
-    npool = st_fl0[1:] - st_fl0[:-1]
+    pu_start = torch.searchsorted(pu_st, st_ids)
+    npool = pu_start[1:] - pu_start[:-1]
     pool_need = int(npool.max()) if nst else 0
-    if pool_need > pool_cap:
+    if pool_need + (pool_need & 1) > pool_cap:
         return None
-    pool_idx = pinv - st_fl0[ts_st]                  # per tile slot
+    pool_idx = pinv - pu_start[ts_st]                # per tile slot
+    # flush tables start at even entries (16-byte aligned TMA source): pad odd pools by one
+    npad = npool + (npool & 1)
+    st_fl0 = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(npad, 0)])
+    fl_pos = st_fl0[pu_st] + (arange(int(pu.shape[0])) - pu_start[pu_st])
     # first touch: the smallest tile of every (super-tile, slot) group stores, later ones add
     first_tile = torch.full((int(pu.shape[0]),), ntiles, dtype=i64, device=dev)
     first_tile.scatter_reduce_(0, pinv, ts_tile, reduce="amin", include_self=True)
@@ -214,17 +220,17 @@ def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, t
 
     def tgt(slots):                      # where a CSR slot's value is written
         return slots if slot_map is None else slot_map[slots]
-    npu = int(pu.shape[0])
-    fl_m = torch.empty(npu, dtype=i64, device=dev)
-    fl_m[o2] = torch.where(shared[grp_of], spos | 0x80000000, tgt(g_sorted))
+    npu = int(st_fl0[-1])
+    fl_m = torch.full((npu + 2,), NONE, dtype=i64, device=dev)       # padding entries: no target
+    fl_m[fl_pos[o2]] = torch.where(shared[grp_of], spos | 0x80000000, tgt(g_sorted))
     mir_sorted = mirror[g_sorted]
-    fl_m2 = torch.empty(npu, dtype=i64, device=dev)
-    fl_m2[o2] = torch.where(shared[grp_of] | (mir_sorted == g_sorted),
-                            torch.full_like(g_sorted, NONE), tgt(mir_sorted))
+    fl_m2 = torch.full((npu + 2,), NONE, dtype=i64, device=dev)
+    fl_m2[fl_pos[o2]] = torch.where(shared[grp_of] | (mir_sorted == g_sorted),
+                                    torch.full_like(g_sorted, NONE), tgt(mir_sorted))
     fp = P1FusedPlan2()
     fp.T, fp.ring, fp.nel, fp.nnz, fp.S = T, ring, nel, nnz, S
     fp.ntiles, fp.nst = ntiles, nst
-    fp.pool_cap = max((pool_need + 1) // 2 * 2, 2)
+    fp.pool_cap = max(pool_need + (pool_need & 1), 2)
     fp.fl = _i32(torch.stack([fl_m, fl_m2], dim=1)).contiguous()   # (npu, 2) uint32 bit patterns
     fp.st_fl0 = st_fl0.contiguous()
     fp.st_tile0 = torch.clamp(st_ids * S, max=ntiles).to(torch.int32).contiguous()
@@ -237,7 +243,7 @@ def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, t
                         ).to(torch.int32).contiguous()
     fp.scratch = torch.empty(max(fp.nscratch, 1), dtype=torch.float64, device=dev)
     fp.npool_total = npu
-    del o2, g_sorted, grp_of, spos, fl_m, fl_m2, mir_sorted, pu, pu_st, pu_gslot
+    del o2, g_sorted, grp_of, spos, fl_m, fl_m2, mir_sorted, pu, pu_st, pu_gslot, fl_pos
     # 6. lanes: long lists (vertex diagonals collect ~24 terms) are split over F = 2 or 4
     # adjacent lanes combined by a fixed shuffle tree; within a tile F-major, then by
     # decreasing chunk length (sliced ELL)
@@ -320,8 +326,11 @@ def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, t
         del sec_tile, sec_pos
     buf32[(rs[vert_tile] + off_verts) // 4 + vert_loc] = vert_gid.to(torch.int32)
     g_local = arange(ngroups) - tile_group_start[grp_tile]
-    gword = (grp_base // 64) | ((grp_len // 2) << 16)
-    buf32[(rs[grp_tile] + off_grp[grp_tile]) // 4 + g_local] = gword.to(torch.int32)
+    # bit 31: the group holds split lists (F > 1), i.e. the kernel must run its shuffle tree
+    grp_split = torch.zeros(ngroups, dtype=i64, device=dev)
+    grp_split.scatter_reduce_(0, grp_of_slot, (F > 1).long(), reduce="amax", include_self=True)
+    gword = (grp_base // 64) | ((grp_len // 2) << 16) | (grp_split << 31)
+    buf32[(rs[grp_tile] + off_grp[grp_tile]) // 4 + g_local] = _i32(gword)
     # lane words: unused lanes 0xFFFF, leaders pool | fsel << 13 | first << 15
     lanes = arange(32)
     buf16[((rs[grp_tile] + off_lane[grp_tile]) // 2 + g_local * 32)[:, None] + lanes[None, :]] = -1
@@ -390,7 +399,9 @@ def finalize(fp, nz=None):
         g = torch.searchsorted(gcum, j, right=True) - 1
         o = j - gcum[g]
         c, lane = o // 32, o % 32
-        buf16[fp._ids_base16[g] + ((c // 2) * 32 + lane) * 2 + (c & 1)] = ell[:n]
+        # stored as byte offsets into the staging array (index * 8 < 65536 for T <= 512)
+        buf16[fp._ids_base16[g] + ((c // 2) * 32 + lane) * 2 + (c & 1)] = \
+            _i16((ell[:n].long() & 0xFFFF) * 8)
         del j, g, o, c, lane
     fp._ell = fp._gcum = fp._grp_len = fp._ids_base16 = None
     if nz is None:
@@ -450,7 +461,7 @@ def build_auto(basis, plan, T=256, ring=3, pool_cap=2048, S=None, slot_map=None,
 def _launch(fp, p, data, stream, mode, nz_out=None):
     code = _lib.lib().skb_p1tet_laplace_fused2(
         p.data_ptr(), p.shape[1], fp.rec.data_ptr(), fp.rec_start.data_ptr(),
-        fp.st_tile0.data_ptr(), fp.st_fl0.data_ptr(), fp.fl.data_ptr(), fp.nst, fp.T, fp.ring,
+        fp.st_fl0.data_ptr(), fp.fl.data_ptr(), fp.nst, fp.ntiles, fp.S, fp.T, fp.ring,
         fp.rec_cap, fp.vcap, fp.pool_cap, fp.ctas_per_sm, mode, C.c_double(fp.w), fp.nqp,
         data.data_ptr(), fp.scratch.data_ptr(), fp.flag.data_ptr(), nz_out, stream)
     _lib.check(code, "skb_p1tet_laplace_fused2")

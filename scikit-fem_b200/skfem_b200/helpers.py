@@ -12,6 +12,18 @@ import numpy as np
 from .field import DeviceArray, _stack
 
 
+def _array(items):
+    """``np.array([...])`` of the reference's helpers.  numpy does not dispatch ``np.array``
+    through ``__array_function__``, so a list of device fields has to be stacked explicitly
+    (user forms: use ``np.stack`` or ``skfem_b200.helpers.array``); host arrays go to numpy."""
+    if any(isinstance(a, DeviceArray) for a in items):
+        return _stack(items)
+    return np.array(items)
+
+
+array = _array
+
+
 def _contract(spec, *ops):
     return np.einsum(spec, *ops)
 
@@ -37,11 +49,11 @@ def curl(u):
     if g is None:
         raise NotImplementedError
     if g.ndim == 3 and g.shape[0] == 2:
-        return np.array([g[1], -g[0]])
+        return _array([g[1], -g[0]])
     if g.ndim == 4 and g.shape[0] == 2:
         return g[1, 0] - g[0, 1]
     if g.ndim == 4 and g.shape[0] == 3:
-        return np.array([g[2, 1] - g[1, 2], g[0, 2] - g[2, 0], g[1, 0] - g[0, 1]])
+        return _array([g[2, 1] - g[1, 2], g[0, 2] - g[2, 0], g[1, 0] - g[0, 1]])
     raise NotImplementedError
 
 
@@ -162,9 +174,9 @@ def cross(A, B):
     if A.shape[0] == 2:
         return A[0] * B[1] - A[1] * B[0]
     if A.shape[0] == 3:
-        return np.array([A[1] * B[2] - A[2] * B[1],
-                         A[2] * B[0] - A[0] * B[2],
-                         A[0] * B[1] - A[1] * B[0]])
+        return _array([A[1] * B[2] - A[2] * B[1],
+                       A[2] * B[0] - A[0] * B[2],
+                       A[0] * B[1] - A[1] * B[0]])
     raise NotImplementedError
 
 

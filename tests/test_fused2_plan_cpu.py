@@ -107,13 +107,16 @@ def _emulate(fp, p):
             lanew = rec16[(base + off_lane) // 2: (base + off_lane) // 2 + 32 * ngroups]
             ids0 = (base + off_ids) // 4
             for g in range(ngroups):
-                rows, off = int(grp[g] >> 16), int(grp[g] & 0xFFFF)
+                rows, off = int(grp[g] >> 16) & 0x7FFF, int(grp[g] & 0xFFFF)
+                split = bool(grp[g] >> 31)
                 w2 = rec[ids0 + off * 32: ids0 + (off + rows) * 32].view(np.uint32).reshape(rows, 32)
-                acc = np.zeros(32)
+                s0, s1 = np.zeros(32), np.zeros(32)
                 for r in range(rows):
                     lo, hi = (w2[r] & 0xFFFF).astype(np.int64), (w2[r] >> 16).astype(np.int64)
-                    assert lo.max() < 10 * T + 16 and hi.max() < 10 * T + 16
-                    acc = (acc + vals[lo]) + vals[hi]
+                    assert (lo % 8 == 0).all() and (hi % 8 == 0).all()   # byte offsets
+                    assert lo.max() < 8 * (10 * T + 16) and hi.max() < 8 * (10 * T + 16)
+                    s0, s1 = s0 + vals[lo // 8], s1 + vals[hi // 8]
+                acc = s0 + s1
                 t1 = acc + np.r_[acc[1:], acc[-1:]]
                 t2 = t1 + np.r_[t1[2:], t1[-2:]]
                 for lane in range(32):
@@ -121,6 +124,7 @@ def _emulate(fp, p):
                     if lw == 0xFFFF:
                         continue
                     fs = (lw >> 13) & 3
+                    assert split or fs == 0
                     res = acc[lane] if fs == 0 else (t1[lane] if fs == 1 else t2[lane])
                     pi = lw & 0x1FFF
                     assert pi < st_fl0[st + 1] - st_fl0[st]
@@ -131,8 +135,12 @@ def _emulate(fp, p):
                         assert not np.isnan(pool[pi])
                         pool[pi] = pool[pi] + res
         # ---- flush ----
+        assert st_fl0[st] % 2 == 0 and st_fl0[st + 1] - st_fl0[st] <= fp.pool_cap
         for i in range(st_fl0[st + 1] - st_fl0[st]):
             m, m2 = int(fl[st_fl0[st] + i, 0]), int(fl[st_fl0[st] + i, 1])
+            if m == NONE:                              # padding entry of an odd pool
+                assert m2 == NONE and np.isnan(pool[i])
+                continue
             assert not np.isnan(pool[i])
             if m & 0x80000000:
                 assert np.isnan(scratch[m & 0x7FFFFFFF])

@@ -43,8 +43,8 @@ def options():
     F._CONFIG.update(saved)
 
 
-@pytest.mark.parametrize("tile,ring,pool,S", [(256, 3, 2048, None), (128, 2, 1024, None),
-                                              (512, 2, 4096, None), (256, 4, 4096, 1),
+@pytest.mark.parametrize("tile,ring,pool,S", [(256, 3, 2048, None), (128, 3, 1024, None),
+                                              (512, 3, 4096, None), (256, 4, 4096, 1),
                                               (128, 3, 2048, 2)])
 def test_fused2_golden_and_oracle(options, tile, ring, pool, S):
     from skfem_b200.models.poisson import laplace

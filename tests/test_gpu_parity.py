@@ -403,3 +403,52 @@ def test_fused_kd_tiling_parity():
             np.testing.assert_allclose(A1.data, ref.data, rtol=1e-12, atol=1e-12 * scale)
     finally:
         set_options(fused_tiling="morton", fused_version=2)
+
+
+def test_plan_cache_is_keyed_on_the_zero_mask():
+    """Traced forms share sparsity plans by zero mask, not by object identity (ADVICE r1:
+    ``id(form)`` keys collide for inline lambdas).  Laplace-like and mass-like lambdas
+    created and dropped on one structured basis (different patterns: 7-point vs 15-point on a
+    Kuhn grid), a form whose closure coefficient changes its pattern between calls, and a
+    coefficient field passed as ``w`` (warm path with kwargs) - each against the oracle."""
+    import gc
+    from oracle import skfem_oracle as O
+    from skfem_b200.helpers import dot, grad
+    g = np.linspace(0, 1, 6)
+    m = fem.MeshTet.init_tensor(g, g, g)
+    om = mesh_of(dict(p=m.p, t=m.t), "tet")
+    b = fem.Basis(m, fem.ElementTetP1())
+    bo = O.cell_basis(om, O.element("tet_p1"))
+
+    def same(A, Ao):
+        assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+        np.testing.assert_allclose(A.data, Ao.data, rtol=RTOL, atol=RTOL * np.abs(Ao.data).max())
+    ref_lap = O.assemble_bilinear(O.laplace, bo)
+    ref_mass = O.assemble_bilinear(O.mass, bo)
+    assert ref_lap.nnz != ref_mass.nnz
+    for _ in range(3):                        # fresh lambdas: ids are recycled by CPython
+        same(fem.BilinearForm(lambda u, v, w: dot(grad(u), grad(v))).assemble(b), ref_lap)
+        gc.collect()
+        same(fem.BilinearForm(lambda u, v, w: u * v).assemble(b), ref_mass)
+        gc.collect()
+    plans = b._plans["by-mask"]
+    assert len(plans) == 2                    # one plan per distinct mask, reused
+    coef = {"c": 0.0}
+    form = fem.BilinearForm(lambda u, v, w: dot(grad(u), grad(v)) + coef["c"] * u * v)
+    same(form.assemble(b), ref_lap)
+    coef["c"] = 2.0                           # same object, new pattern
+
+    def both(u, v, w):
+        return O.dot(O.grad(u), O.grad(v)) + 2.0 * u * v
+    same(form.assemble(b), O.assemble_bilinear(both, bo))
+    # kwargs no longer disable the cache: a coefficient field, assembled twice
+    kform = fem.BilinearForm(lambda u, v, w: w["k"] * dot(grad(u), grad(v)))
+    kdofs = 1.0 + m.p[0] * m.p[1]
+    A1 = kform.assemble(b, k=kdofs)
+    n_before = len(b._plans["by-mask"])
+    A2 = kform.assemble(b, k=kdofs)
+    assert len(b._plans["by-mask"]) == n_before and np.array_equal(A1.data, A2.data)
+
+    def kref(u, v, w):
+        return w["k"] * O.dot(O.grad(u), O.grad(v))
+    same(A1, O.assemble_bilinear(kref, bo, k=O.interpolate(bo, kdofs)))

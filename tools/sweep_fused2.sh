@@ -23,20 +23,17 @@ while read -r line; do
   [ -z "$line" ] && continue
   run $line
 done <<'CFG'
---fused-version 1
 --tile2 256 --ring2 3 --pool 2048
---tile2 256 --ring2 3 --pool 4096
---tile2 256 --ring2 2 --pool 2048
 --tile2 256 --ring2 4 --pool 2048
---tile2 512 --ring2 2 --pool 4096
+--tile2 256 --ring2 3 --pool 4096
+--tile2 512 --ring2 3 --pool 4096
 --tile2 512 --ring2 3 --pool 2048
+--tile2 512 --ring2 4 --pool 4096
 --tile2 128 --ring2 3 --pool 2048
---tile2 128 --ring2 4 --pool 1024
---tile2 256 --ring2 3 --pool 2048 --ctas 2
 --tile2 256 --ring2 3 --pool 2048 --debug-flags 1
 --tile2 256 --ring2 3 --pool 2048 --debug-flags 2
 --tile2 256 --ring2 3 --pool 2048 --debug-flags 3
---tile2 256 --ring2 3 --pool 2048 --debug-flags 64
+--tile2 256 --ring2 3 --pool 2048 --debug-flags 67
 --tile2 256 --ring2 3 --pool 2048 --arith fast
 CFG
 cat $out
