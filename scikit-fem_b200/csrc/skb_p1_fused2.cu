@@ -106,11 +106,6 @@ __device__ __forceinline__ void tma_bulk_g2s2(void *dst, const void *src, unsign
 __device__ __forceinline__ void cp_async8_2(uint32_t dst_smem, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
 
 __device__ __forceinline__ unsigned nonzero_bits(double v) {   // v != +-0, integer pipe only
   return (((unsigned)__double2hiint(v) & 0x7fffffffu) | (unsigned)__double2loint(v)) != 0u;
@@ -222,8 +217,6 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
 
   const double w1 = a.w;
   const double w4 = a.w * 4.0;
-  const uint32_t vals_s = smem_u32_2(vals);
-  const uint32_t pool_s = smem_u32_2(pool);
   unsigned bad = 0;
   int slot = 0, par = 0;
   bool first_of_st = false;             // the first super-tile's flush table is already in flight
@@ -243,17 +236,15 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
       const ushort4 v = reinterpret_cast<const ushort4 *>(r + sizeof(RecHeader2))[tid];
       if (v.x != 0xFFFF) {   // not a padding element of a short tile
         const unsigned keep = (unsigned)(v.x >> 10) | ((unsigned)(v.y >> 10) << 6);
-        const uint32_t cb = smem_u32_2(coords + (size_t)par * 3 * a.vcap);
-        const uint32_t c0 = cb + 24u * (v.x & 0x3ffu), c1 = cb + 24u * (v.y & 0x3ffu),
-                       c2 = cb + 24u * (v.z & 0x3ffu), c3 = cb + 24u * (v.w & 0x3ffu);
+        const double *cb = coords + (par ? 3 * a.vcap : 0);
+        const double *c0 = cb + 3u * (v.x & 0x3ffu), *c1 = cb + 3u * (v.y & 0x3ffu),
+                     *c2 = cb + 3u * (v.z & 0x3ffu), *c3 = cb + 3u * (v.w & 0x3ffu);
         double A[3][3];
         {
-          const double x0 = lds_f64(c0), y0 = lds_f64(c0 + 8), z0 = lds_f64(c0 + 16);
-          A[0][0] = lds_f64(c1) - x0; A[0][1] = lds_f64(c2) - x0; A[0][2] = lds_f64(c3) - x0;
-          A[1][0] = lds_f64(c1 + 8) - y0; A[1][1] = lds_f64(c2 + 8) - y0;
-          A[1][2] = lds_f64(c3 + 8) - y0;
-          A[2][0] = lds_f64(c1 + 16) - z0; A[2][1] = lds_f64(c2 + 16) - z0;
-          A[2][2] = lds_f64(c3 + 16) - z0;
+          const double x0 = c0[0], y0 = c0[1], z0 = c0[2];
+          A[0][0] = c1[0] - x0; A[0][1] = c2[0] - x0; A[0][2] = c3[0] - x0;
+          A[1][0] = c1[1] - y0; A[1][1] = c2[1] - y0; A[1][2] = c3[1] - y0;
+          A[2][0] = c1[2] - z0; A[2][1] = c2[2] - z0; A[2][2] = c3[2] - z0;
         }
         double det, n[3][3], inv[3][3];
         if (MODE == 3) {
@@ -316,7 +307,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
         const double dx = adet * w1;            // cell_basis.py:104-105
         const double dx4 = adet * w4;           // == 4 * dx exactly (power-of-two scaling)
         unsigned nz = 0;
-        const uint32_t out_s = vals_s + 8u * tid;
+        double *out = vals + tid;
         int k = 0;
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp)
@@ -341,8 +332,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
               }
             }
             nz |= nonzero_bits(val) << k;
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(out_s + 8u * (unsigned)(k * T)), "d"(val)
-                         : "memory");
+            out[k * T] = val;
           }
         bad |= (nz ^ keep);
         if (a.nz_out) a.nz_out[(size_t)tile * T + tid] = (uint16_t)nz;
@@ -363,22 +353,43 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
       const int ngroups = (int)h->ngroups;
       const uint32_t *grp = reinterpret_cast<const uint32_t *>(r + h->off_grp);
       const uint16_t *lanew = reinterpret_cast<const uint16_t *>(r + h->off_lane) + lane;
-      const uint32_t *ids = reinterpret_cast<const uint32_t *>(r + h->off_ids) + lane;
+      const unsigned char *ids = r + h->off_ids + 4 * lane;
+      const unsigned char *vb = reinterpret_cast<const unsigned char *>(vals);
+      // the id words hold two byte offsets into vals; a lane's even and odd columns are summed
+      // separately (s0, s1), rows 2 apart alternate between two more accumulators
+#define SKB_V(off) (*reinterpret_cast<const double *>(vb + (off)))
+#define SKB_W(row) (*reinterpret_cast<const uint32_t *>(cb + 128u * (row)))
 #pragma unroll 1
       for (int gi = warp; gi < ngroups; gi += NW) {
         const uint32_t gw = grp[gi];
-        const int rows = (int)((gw >> 16) & 0x7fffu);      // two ELL columns per row
-        const uint32_t *cb = ids + (size_t)(gw & 0xffffu) * 32;
+        int rows = (int)((gw >> 16) & 0x7fffu);            // two ELL columns per row, >= 1
+        const unsigned char *cb = ids + ((gw & 0xffffu) << 7);
         const unsigned lw = lanew[gi * 32];
-        // the words hold byte offsets into vals; even and odd columns are summed separately
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll 2
-        for (int c = 0; c < rows; ++c) {
-          const uint32_t w2 = cb[c * 32];
-          s0 = s0 + lds_f64(vals_s + (w2 & 0xffffu));
-          s1 = s1 + lds_f64(vals_s + (w2 >> 16));
+        double acc;
+        if (rows == 1) {
+          const uint32_t w0 = SKB_W(0);
+          acc = SKB_V(w0 & 0xffffu) + SKB_V(w0 >> 16);
+        } else if (rows == 2) {
+          const uint32_t w0 = SKB_W(0), w1 = SKB_W(1);
+          const double a0 = SKB_V(w0 & 0xffffu), a1 = SKB_V(w0 >> 16);
+          const double b0 = SKB_V(w1 & 0xffffu), b1 = SKB_V(w1 >> 16);
+          acc = (a0 + b0) + (a1 + b1);
+        } else {
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 1
+          for (; rows >= 2; rows -= 2, cb += 256) {
+            const uint32_t w0 = SKB_W(0), w1 = SKB_W(1);
+            const double a0 = SKB_V(w0 & 0xffffu), a1 = SKB_V(w0 >> 16);
+            const double b0 = SKB_V(w1 & 0xffffu), b1 = SKB_V(w1 >> 16);
+            s0 = s0 + a0; s1 = s1 + a1; s2 = s2 + b0; s3 = s3 + b1;
+          }
+          if (rows) {
+            const uint32_t w0 = SKB_W(0);
+            s0 = s0 + SKB_V(w0 & 0xffffu);
+            s1 = s1 + SKB_V(w0 >> 16);
+          }
+          acc = (s0 + s2) + (s1 + s3);
         }
-        double acc = s0 + s1;
         if (gw & 0x80000000u) {
           // long lists are split over 2 or 4 adjacent lanes: fixed combination tree
           // (l + l+1) + (l+2 + l+3), selected by the leader lane
@@ -388,11 +399,14 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
           acc = fs == 0 ? acc : (fs == 1 ? t1 : t2);
         }
         if (lw != 0xFFFFu) {
-          const uint32_t pa = pool_s + ((lw & 0x1fffu) << 3);
-          if (!(lw & 0x8000u)) acc = lds_f64(pa) + acc;    // not the first tile touching it
-          asm volatile("st.shared.f64 [%0], %1;" ::"r"(pa), "d"(acc) : "memory");
+          double *pa = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(pool) +
+                                                  ((lw & 0x1fffu) << 3));
+          if (!(lw & 0x8000u)) acc = *pa + acc;            // not the first tile touching it
+          *pa = acc;
         }
       }
+#undef SKB_V
+#undef SKB_W
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // (B) vals, record `slot` free; coords of the next tile visible; pool updated

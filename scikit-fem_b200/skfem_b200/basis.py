@@ -241,7 +241,7 @@ class CellBasis(AbstractBasis):
         self._devcache[key] = d
         return d
 
-    def update_points(self, p, host=True):
+    def update_points(self, p, host=True, adopt=False):
         """Move the mesh: new vertex coordinates ``p`` (``(dim, npts)`` numpy array or device
         tensor), same connectivity.  The reference has no such call - a moved mesh is a new
         ``Mesh`` + ``Basis`` (e.g. inside the Newton / time loops of docs/examples/ex10.py-style
@@ -252,7 +252,11 @@ class CellBasis(AbstractBasis):
         compares the zero mask of every local matrix with the plan's and re-plans when the
         value-dependent pattern (coo_data.py:35) may have changed; all other cached plans are
         discarded, so those forms take the cold path once.  ``host=False`` skips refreshing
-        ``mesh.p`` (the host copy then lags behind until the next call with ``host=True``)."""
+        ``mesh.p`` (the host copy then lags behind until the next call with ``host=True``).
+        ``adopt=True`` (device tensors only): no copy at all - the basis and its mesh reference
+        ``p`` itself from now on (the caller must keep it alive and unchanged until the next
+        ``update_points``); this is how a loop alternating between coordinate buffers, or one
+        CUDA graph per buffer, avoids the device-to-device copy."""
         torch = _torch()
         d = self._dev()
         src = p if torch.is_tensor(p) else torch.from_numpy(
@@ -260,7 +264,16 @@ class CellBasis(AbstractBasis):
         if tuple(src.shape) != tuple(d["p"].shape):
             raise ValueError("update_points: expected an array of shape {}".format(
                 tuple(d["p"].shape)))
-        d["p"].copy_(src, non_blocking=True)
+        if adopt:
+            if not (torch.is_tensor(p) and p.device == d["p"].device and p.is_contiguous()
+                    and p.dtype == torch.float64):
+                raise ValueError("update_points(adopt=True) needs a contiguous float64 tensor "
+                                 "on the basis' device")
+            d["p"] = p
+            d["space"].p = p.data_ptr()
+            self.mesh._dev[str(d["device"])] = (p, d["t"])
+        else:
+            d["p"].copy_(src, non_blocking=True)
         if host:
             self.mesh.p[...] = src.cpu().numpy() if torch.is_tensor(p) else p
         self._fields.clear()
@@ -272,6 +285,7 @@ class CellBasis(AbstractBasis):
         for k, fp in self._plans.items():
             if isinstance(k, tuple) and k and k[0] == "fused" and getattr(fp, "version", 1) == 2:
                 fp.mode = fused2.arithmetic_mode(d["p"], fp.w, fp.nqp)
+                fp.p = d["p"]
                 fp.unchecked = True
                 keep[k] = fp
                 keep[k[1]] = self._plans[k[1]]
