@@ -30,14 +30,27 @@ def _global_mesh(cxy, cz, world):
     return O.mesh_tet_tensor(x, x, z)
 
 
-def _worker(rank, world, port, cxy, cz, out):
+def _worker(rank, world, port, cxy, cz, out, use_partition=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import skfem_oracle as O
-        from skfem_b200.distributed import InterfaceExchange, slab_mesh_tet, balanced_ranges
-        m, l2g, N, ranges = slab_mesh_tet(cxy, cz, rank, world)
+        from skfem_b200.distributed import (InterfaceExchange, slab_mesh_tet, balanced_ranges,
+                                            partition)
+        if use_partition:
+            # one global mesh cut by owning row range (configs[4] style): every element once,
+            # vertices renumbered ascending, contributions only to own or higher ranks' rows
+            import skfem_b200 as fem
+            gm = _global_mesh(cxy, cz, world)
+            m, l2g, N, ranges = partition(fem.MeshTet(gm.p, gm.t), world, rank)
+            counts = [partition(fem.MeshTet(gm.p, gm.t), world, r)[0].nelements
+                      for r in range(world)]
+            assert sum(counts) == gm.t.shape[1] and max(counts) - min(counts) <= 0.2 * max(counts)
+            assert np.all(np.diff(l2g) > 0) and ranges[0] == 0 and ranges[-1] == gm.p.shape[1]
+            assert l2g.min() >= ranges[rank]
+        else:
+            m, l2g, N, ranges = slab_mesh_tet(cxy, cz, rank, world)
         Aloc = O.assemble_bilinear(O.laplace, O.cell_basis(mesh_of(dict(p=m.p, t=m.t), "tet"),
                                                            O.element("tet_p1")))
         lrow = np.repeat(np.arange(Aloc.shape[0]), np.diff(Aloc.indptr))
@@ -59,7 +72,7 @@ def _worker(rank, world, port, cxy, cz, out):
         assert np.array_equal(ex.indices.numpy(), blk.indices)
         np.testing.assert_allclose(d1.numpy(), blk.data, rtol=1e-12,
                                    atol=1e-12 * np.abs(blk.data).max())
-        assert ex.bytes_per_exchange > 0 or rank == world - 1   # the top slab only receives
+        assert ex.bytes_per_exchange > 0 or rank == world - 1   # the top part only receives
         assert list(balanced_ranges(10, 3)) == [0, 4, 7, 10]
         out[rank] = 1
     finally:
@@ -71,4 +84,14 @@ def test_interface_exchange_gloo(world):
     port = _free_port()
     out = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, 5, 3, out), nprocs=world, join=True)
+    assert sorted(out.keys()) == list(range(world))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_range_partition_gloo(world):
+    """distributed.partition (BASELINE configs[4]): the row blocks assembled from the parts of
+    one global mesh equal the serial oracle CSR."""
+    port = _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, 5, 3, out, True), nprocs=world, join=True)
     assert sorted(out.keys()) == list(range(world))

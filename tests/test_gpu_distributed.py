@@ -66,6 +66,10 @@ def _worker(rank, world, port, cxy, cz, out):
             torch.cuda.synchronize()
             for A in last:
                 assert torch.equal(A.data, A2.data), kw
+        # the same check bench.py prints as `parity` at N > 1 (all modes, slab + partition)
+        from skfem_b200.distributed import parity_check
+        par = parity_check(rank, world)
+        assert par["ok"], par
         out[rank] = 1
     finally:
         dist.destroy_process_group()

@@ -202,3 +202,35 @@ def test_fused2_baseline_config2_full_size(options):
     assert np.array_equal(A2.indices, A0.indices)
     u = 2.0 * b.mesh.p[0] - 3.0 * b.mesh.p[1] + 0.5 * b.mesh.p[2]
     np.testing.assert_allclose(u @ (A2 @ u), 13.25 * float(np.prod(s)), rtol=1e-11)
+
+
+def test_full_size_c2_against_the_real_reference(options):
+    """BASELINE configs[1] at full size (6.0 M tets) against the UNMODIFIED reference shipped
+    in oracle/_ref (tools/install_ref.sh): indptr / indices bit-exact, values rtol 1e-12, for
+    the cold (generic) and the warm (fused) path.  About 30 s and 8 GB of host memory."""
+    import os
+    import sys
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "skfem")):
+        pytest.skip("oracle/_ref not installed (tools/install_ref.sh)")
+    sys.path.insert(0, ref)
+    try:
+        import skfem
+        from skfem.models.poisson import laplace as ref_laplace
+        n = 100
+        x = np.linspace(0, 1, n + 1)
+        mr = skfem.MeshTet.init_tensor(x, x, x)
+        Ar = skfem.BilinearForm(ref_laplace.form, nthreads=min(os.cpu_count() or 1, 8)).assemble(
+            skfem.Basis(mr, skfem.ElementTetP1()))
+    finally:
+        sys.path.remove(ref)
+    from skfem_b200.models.poisson import laplace
+    options(fused=True, fused_version=2)
+    m = fem.MeshTet.init_tensor(x, x, x)
+    assert np.array_equal(m.p, mr.p) and np.array_equal(m.t, mr.t)
+    b = fem.Basis(m, fem.ElementTetP1())
+    for A in (laplace.assemble(b), laplace.assemble(b)):      # cold, then warm (fused)
+        assert A.nnz == Ar.nnz == 7150901
+        assert np.array_equal(A.indptr, Ar.indptr) and np.array_equal(A.indices, Ar.indices)
+        np.testing.assert_allclose(A.data, Ar.data, rtol=1e-12, atol=1e-12 * np.abs(Ar.data).max())
+    assert _fused_plan(b) is not None

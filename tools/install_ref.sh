@@ -15,6 +15,4 @@ mkdir -p "$here/oracle/_ref"
 rm -rf "$here/oracle/_ref/skfem"
 cp -r "$src/skfem" "$here/oracle/_ref/skfem"
 find "$here/oracle/_ref" -name __pycache__ -type d -prune -exec rm -rf {} +
-mkdir -p "$here/oracle/_ref/docs_examples"
-cp "$src/docs/examples/performance.py" "$here/oracle/_ref/docs_examples/performance.py"
 echo "install_ref: $(du -sh "$here/oracle/_ref" | cut -f1) in oracle/_ref"
