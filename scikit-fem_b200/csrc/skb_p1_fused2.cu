@@ -126,8 +126,9 @@ __device__ __forceinline__ unsigned nonzero_bits(double v) {   // v != +-0, inte
 // issues the TMA copies, so the latency of its global loads never delays a compute warp.
 // The CTA processes the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ...; its j-th tile
 // uses record buffer j % NR.
-template <int T, int MODE>
-__global__ void __launch_bounds__(T + 32, T >= 512 ? 2 : (T >= 256 ? 3 : 6))
+// NT compute threads handle T / NT elements each (NT == T: one element per thread).
+template <int T, int MODE, int NT = T>
+__global__ void __launch_bounds__(NT + 32, (T >= 512 ? 2 : (T >= 256 ? 3 : 6)))
 p1tet_laplace_fused2_kernel(const P1v2Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NVALS = 10 * T + 16;     // + one staged 0.0 per bank pair
@@ -140,9 +141,10 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
   uint64_t *mbar = reinterpret_cast<uint64_t *>(recs + (size_t)NR * a.rec_cap);   // [NR + 1]
   int *fl_np = reinterpret_cast<int *>(mbar + NR + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = T / 32;
-  const bool is_compute = tid < T;
-  const bool is_producer = tid == T;
+  constexpr int NW = NT / 32;
+  static_assert(T % NT == 0, "elements per compute thread must be integral");
+  const bool is_compute = tid < NT;
+  const bool is_producer = tid == NT;
   const int S = a.S, G = (int)gridDim.x;
 
   // this CTA's tile sequence
@@ -190,7 +192,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
     const uint32_t dst = smem_u32_2(coords + (size_t)par * 3 * a.vcap);
     const double *px = a.p, *py = a.p + a.npts, *pz = a.p + 2 * a.npts;
 #pragma unroll 1
-    for (int i = tid; i < nv; i += T) {
+    for (int i = tid; i < nv; i += NT) {
       const int32_t gv = verts[i];
       cp_async8_2(dst + 24 * i, px + gv);
       cp_async8_2(dst + 24 * i + 8, py + gv);
@@ -233,7 +235,9 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
     if (is_compute && has_next) gather(recs + (size_t)slot1 * a.rec_cap, par ^ 1);
     // ---- P1: local matrix of element `tid` -> vals -------------------------------------
     if (is_compute && !(a.debug & 1)) {
-      const ushort4 v = reinterpret_cast<const ushort4 *>(r + sizeof(RecHeader2))[tid];
+#pragma unroll 1
+     for (int el = tid; el < T; el += NT) {
+      const ushort4 v = reinterpret_cast<const ushort4 *>(r + sizeof(RecHeader2))[el];
       if (v.x != 0xFFFF) {   // not a padding element of a short tile
         const unsigned keep = (unsigned)(v.x >> 10) | ((unsigned)(v.y >> 10) << 6);
         const double *cb = coords + (par ? 3 * a.vcap : 0);
@@ -307,7 +311,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
         const double dx = adet * w1;            // cell_basis.py:104-105
         const double dx4 = adet * w4;           // == 4 * dx exactly (power-of-two scaling)
         unsigned nz = 0;
-        double *out = vals + tid;
+        double *out = vals + el;
         int k = 0;
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp)
@@ -335,8 +339,9 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
             out[k * T] = val;
           }
         bad |= (nz ^ keep);
-        if (a.nz_out) a.nz_out[(size_t)tile * T + tid] = (uint16_t)nz;
+        if (a.nz_out) a.nz_out[(size_t)tile * T + el] = (uint16_t)nz;
       }
+     }
     }
     __syncthreads();   // (A) vals complete
     if (is_producer) {
@@ -415,7 +420,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
     if (last_of_st && is_compute && !(a.debug & 64)) {
       const int np = *fl_np;
 #pragma unroll 2
-      for (int i = tid; i < np; i += T) {
+      for (int i = tid; i < np; i += NT) {
         const uint2 m = flbuf[i];
         const double val = pool[i];
         if (m.x != 0xffffffffu) {
@@ -456,20 +461,20 @@ p1_combine2_kernel(const double *__restrict__ scratch, const uint32_t *__restric
   }
 }
 
-template <int T, int MODE>
+template <int T, int MODE, int NT = T>
 static int launch_fused2(const P1v2Args &a, size_t smem, int sms, int ctas_per_sm,
                          cudaStream_t st) {
-  auto k = p1tet_laplace_fused2_kernel<T, MODE>;
+  auto k = p1tet_laplace_fused2_kernel<T, MODE, NT>;
   SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  SKB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T + 32, smem));
+  SKB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NT + 32, smem));
   if (occ < 1) return SKB_ETOOBIG;
   if (ctas_per_sm > 0 && occ > ctas_per_sm) occ = ctas_per_sm;
   int free_sms = sm_reserve();
   if (free_sms > sms - 1) free_sms = sms - 1;
   const int cap = occ * (sms - free_sms);
   const int grid = a.nst < cap ? a.nst : cap;
-  k<<<grid, T + 32, smem, st>>>(a);
+  k<<<grid, NT + 32, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -527,9 +532,18 @@ extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const voi
     else if (mode == 2) rc = launch_fused2<TT, 2>(a, smem, sms, ctas_per_sm, st);        \
     else rc = launch_fused2<TT, 3>(a, smem, sms, ctas_per_sm, st);                       \
   }
-  SKB_P1V2_CASE(128)
-  SKB_P1V2_CASE(256)
-  SKB_P1V2_CASE(512)
+  const int ept = ctas_per_sm >> 8;        // bits 8..: elements per compute thread (0/1 = one)
+  ctas_per_sm &= 0xff;
+  if (ept <= 1) {
+    SKB_P1V2_CASE(128)
+    SKB_P1V2_CASE(256)
+    SKB_P1V2_CASE(512)
+  } else if (ept == 2 && tile_elems == 512) {
+    if (mode == 0) rc = launch_fused2<512, 0, 256>(a, smem, sms, ctas_per_sm, st);
+    else if (mode == 1) rc = launch_fused2<512, 1, 256>(a, smem, sms, ctas_per_sm, st);
+    else if (mode == 2) rc = launch_fused2<512, 2, 256>(a, smem, sms, ctas_per_sm, st);
+    else rc = launch_fused2<512, 3, 256>(a, smem, sms, ctas_per_sm, st);
+  }
 #undef SKB_P1V2_CASE
   if (rc == SKB_OK) count_launch();
   return rc;

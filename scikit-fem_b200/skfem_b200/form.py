@@ -68,7 +68,7 @@ _CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring":
            "fused_arith": "exact", "fused_spread": True, "fused_renumber": True,
            "fused_l2_persist": True, "fused_tiling": "morton",
            "fused_version": 2, "fused2_tile": 256, "fused2_ring": 3, "fused2_pool": 2048,
-           "fused2_ctas": 0, "fused2_S": None}
+           "fused2_ctas": 0, "fused2_S": None, "fused2_ept": 1}
 
 
 def set_options(**kw):
@@ -513,7 +513,8 @@ class BilinearForm(Form):
                                            S=_CONFIG["fused2_S"], slot_map=slot_map,
                                            spread=bool(_CONFIG["fused_spread"]),
                                            renumber=bool(_CONFIG["fused_renumber"]),
-                                           ctas_per_sm=int(_CONFIG["fused2_ctas"]))
+                                           ctas_per_sm=int(_CONFIG["fused2_ctas"]) |
+                                           (int(_CONFIG["fused2_ept"]) << 8))
                     ubasis._plans[fkey] = fp
                 if fp is False:
                     fp = fused.build_auto(ubasis, plan, T=fused_tile(),
