@@ -183,13 +183,7 @@ int skb_p1_combine(const double *scratch, const uint32_t *sptr, const uint32_t *
  * pool_cap accumulators in shared memory, one per canonical CSR slot of the super-tile; after
  * the last tile the pool is flushed in CSR order through the flush table fl (uint32 pairs
  * {CSR slot, or bit31 | scratch position, or 0xFFFFFFFF for a padding entry; mirror slot or
- * 0xFFFFFFFF}, st_fl0[s] = first entry of super-tile s, always even; fetched by TMA).
- * Slots shared between super-tiles go through scratch (grouped by slot, super-tiles ascending:
- * partials of shared slot k at [sptr[k], sptr[k+1])) and are added in that order either by
- * skb_p1_combine2 (cnt == NULL) or inside the kernel by whichever super-tile stores the last
- * partial of the slot (cnt: nshared zero-initialised arrival counters, reset by the kernel; the
- * second word of a shared slot's flush entry is then k) - the same sum either way, no float
- * atomics.
+ * 0xFFFFFFFF}, st_fl0[s] = first entry of super-tile s, always even; fetched by TMA).  Only slots shared between super-tiles go through scratch + skb_p1_combine2.
  * mode: 0 any coordinates / any equal-weight rule (IEEE division), 1 nqp == 4 and coordinates
  * 0 or within [2^-60, 2^60] (shared reciprocal + Markstein corrections == IEEE division),
  * 2 additionally coordinates within [2^-28, 2^28] and w within [2^-20, 1] (the quadrature sum
@@ -210,8 +204,7 @@ int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
                              int32_t tile_elems, int32_t ring, int32_t rec_cap, int32_t vcap,
                              int32_t pool_cap, int32_t ctas_per_sm, int32_t mode, double w,
                              int32_t nqp, double *csr_data, double *scratch, int32_t *flag,
-                             uint16_t *nz_out, const uint32_t *sptr, const uint32_t *gslot,
-                             const uint32_t *gslot2, uint32_t *cnt, void *stream);
+                             uint16_t *nz_out, void *stream);
 int skb_p1_combine2(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
                     const uint32_t *gslot2, int64_t nshared, double *csr_data, void *stream);
 

@@ -56,9 +56,6 @@ struct P1v2Args {
   int32_t debug;
   int32_t *flag;                // device int: bit0 set when the zero mask of an element changed
   uint16_t *nz_out;             // plan time only: receives the zero mask of every element
-  // in-kernel combine of the slots shared between super-tiles (NULL cnt: skb_p1_combine2 does it)
-  const uint32_t *sptr, *gslot, *gslot2;
-  uint32_t *cnt;                // [nshared] arrival counters, zero between launches
 };
 
 struct RecHeader2 {             // 32 bytes at the start of every record
@@ -420,57 +417,16 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
     __syncthreads();   // (B) vals, record `slot` free; coords of the next tile visible; pool updated
     if (is_producer) issue_record();
     // ---- flush: the super-tile's pool -> csr_data / scratch, in CSR order --------------------
-    // Slots shared with other super-tiles: the partial goes to its place in `scratch` (grouped
-    // by slot, super-tiles ascending); whoever stores the last partial of a slot (arrival
-    // counter) adds them all in that fixed order - the sum does not depend on who is last -
-    // and writes the CSR slot and its mirror.  Four entries per thread and round, so that the
-    // fences / atomics / partial loads of different entries overlap.
     if (last_of_st && is_compute && !(a.debug & 64)) {
       const int np = *fl_np;
-#pragma unroll 1
-      for (int base = tid; base < np; base += 4 * NT) {
-        uint2 m[4];
-        double val[4];
-        bool any_shared = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = base + j * NT;
-          m[j] = make_uint2(0xffffffffu, 0xffffffffu);
-          if (i < np) { m[j] = flbuf[i]; val[j] = pool[i]; }
-          if (m[j].x != 0xffffffffu) {
-            if (m[j].x & 0x80000000u) {
-              a.scratch[m[j].x & 0x7fffffffu] = val[j];
-              any_shared = true;
-            } else {
-              a.csr_data[m[j].x] = val[j];
-              if (m[j].y != 0xffffffffu) a.csr_data[m[j].y] = val[j];
-            }
-          }
-        }
-        if (a.cnt != nullptr && any_shared) {
-          __threadfence();
-          unsigned lo[4], n[4], old[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            n[j] = 0;
-            if (m[j].x != 0xffffffffu && (m[j].x & 0x80000000u)) {
-              lo[j] = a.sptr[m[j].y];
-              n[j] = a.sptr[m[j].y + 1] - lo[j];
-              old[j] = atomicAdd(a.cnt + m[j].y, 1u);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n[j] != 0 && old[j] == n[j] - 1) {       // last arriver of this slot
-              __threadfence();
-              double acc = __ldcg(a.scratch + lo[j]);
-              for (unsigned i = 1; i < n[j]; ++i) acc = acc + __ldcg(a.scratch + lo[j] + i);
-              const uint32_t s1 = a.gslot[m[j].y], s2 = a.gslot2[m[j].y];
-              a.csr_data[s1] = acc;
-              if (s2 != s1) a.csr_data[s2] = acc;
-              a.cnt[m[j].y] = 0;
-            }
-          }
+#pragma unroll 2
+      for (int i = tid; i < np; i += NT) {
+        const uint2 m = flbuf[i];
+        const double val = pool[i];
+        if (m.x != 0xffffffffu) {
+          if (m.x & 0x80000000u) a.scratch[m.x & 0x7fffffffu] = val;
+          else a.csr_data[m.x] = val;
+          if (m.y != 0xffffffffu) a.csr_data[m.y] = val;
         }
       }
       // the next super-tile's first pool write comes after barrier (A) of its first tile
@@ -538,10 +494,6 @@ extern "C" int64_t skb_p1_fused2_smem_bytes(int32_t tile_elems, int32_t ring, in
 // reference's pattern and the caller must re-plan (coo_data.py:35, eliminate_zeros).
 // nz_out != NULL (plan time): only the local matrices are formed and the 10-bit zero mask of
 // element e of tile t is stored at nz_out[t * tile_elems + e]; nothing else is written.
-// cnt != NULL: slots shared between super-tiles are combined inside this kernel by the last
-// arriving super-tile (sptr / gslot / gslot2 as for skb_p1_combine2, cnt: nshared zeroed
-// counters, left zero again); the flush entries of shared slots then carry the slot's index
-// into sptr in their second word.  cnt == NULL: the caller runs skb_p1_combine2 afterwards.
 extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
                                         const uint64_t *rec_start, const int64_t *st_fl0,
                                         const void *fl, int32_t nst, int32_t ntiles,
@@ -550,8 +502,7 @@ extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const voi
                                         int32_t vcap, int32_t pool_cap, int32_t ctas_per_sm,
                                         int32_t mode, double w, int32_t nqp, double *csr_data,
                                         double *scratch, int32_t *flag, uint16_t *nz_out,
-                                        const uint32_t *sptr, const uint32_t *gslot,
-                                        const uint32_t *gslot2, uint32_t *cnt, void *stream) {
+                                        void *stream) {
   using namespace skb;
   if (nst < 0 || !p || nqp <= 0 || vcap <= 0 || (vcap & 1) || pool_cap <= 0 || (pool_cap & 1) ||
       rec_cap <= 0 || (rec_cap & 15) || ring < 3 || ring > 8 || !flag || tiles_per_super < 1 ||
@@ -566,8 +517,6 @@ extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const voi
   a.rec_cap = rec_cap; a.vcap = vcap; a.pool_cap = pool_cap; a.ring = ring;
   a.csr_data = csr_data; a.scratch = scratch; a.w = w; a.nqp = nqp;
   a.debug = debug_flags(); a.flag = flag; a.nz_out = nz_out;
-  a.sptr = sptr; a.gslot = gslot; a.gslot2 = gslot2; a.cnt = cnt;
-  if (cnt && (!sptr || !gslot || !gslot2)) return SKB_EINVAL;
   if (nz_out) a.debug |= 2 | 64;     // plan-time mask pass: local matrices only
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;

@@ -33,9 +33,7 @@ a *pool* of accumulators in shared memory, one per canonical slot it touches, nu
 CSR order.  After the last tile of a super-tile the pool is flushed through the
 super-tile's *flush table* ``fl`` (uint32 pairs): slots touched by this super-tile only go
 straight to ``csr_data`` (and the mirror slot), the others to ``scratch`` (grouped by CSR
-slot, super-tiles ascending); the super-tile that stores the last partial of a slot (an
-integer arrival counter per shared slot) adds them in that fixed order and writes the slot
-and its mirror - or, with ``fp.inkernel_combine = False``, ``skb_p1_combine2`` does.
+slot, super-tiles ascending) and are added by ``skb_p1_combine2``.
 
 The preprocessing uses torch sort / unique / searchsorted (cold path, plumbing); the warm
 path runs only this package's kernels.
@@ -226,13 +224,9 @@ def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, t
     fl_m = torch.full((npu + 2,), NONE, dtype=i64, device=dev)       # padding entries: no target
     fl_m[fl_pos[o2]] = torch.where(shared[grp_of], spos | 0x80000000, tgt(g_sorted))
     mir_sorted = mirror[g_sorted]
-    # second word: the mirror slot of an exclusive off-diagonal slot; for a shared slot its
-    # index k into sptr / gslot / gslot2 (in-kernel combine by the last arriving super-tile)
-    shared_rank = torch.cumsum(shared.long(), 0) - 1
     fl_m2 = torch.full((npu + 2,), NONE, dtype=i64, device=dev)
-    fl_m2[fl_pos[o2]] = torch.where(
-        shared[grp_of], shared_rank[grp_of],
-        torch.where(mir_sorted == g_sorted, torch.full_like(g_sorted, NONE), tgt(mir_sorted)))
+    fl_m2[fl_pos[o2]] = torch.where(shared[grp_of] | (mir_sorted == g_sorted),
+                                    torch.full_like(g_sorted, NONE), tgt(mir_sorted))
     fp = P1FusedPlan2()
     fp.T, fp.ring, fp.nel, fp.nnz, fp.S = T, ring, nel, nnz, S
     fp.ntiles, fp.nst = ntiles, nst
@@ -248,8 +242,6 @@ def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, t
     fp.sptr = torch.cat([gstart[sh], torch.tensor([fp.nscratch], device=dev, dtype=i64)]
                         ).to(torch.int32).contiguous()
     fp.scratch = torch.empty(max(fp.nscratch, 1), dtype=torch.float64, device=dev)
-    fp.cnt = torch.zeros(max(fp.nshared, 1), dtype=torch.int32, device=dev)
-    fp.inkernel_combine = True
     fp.npool_total = npu
     del o2, g_sorted, grp_of, spos, fl_m, fl_m2, mir_sorted, pu, pu_st, pu_gslot, fl_pos
     # 6. lanes: long lists (vertex diagonals collect ~24 terms) are split over F = 2 or 4
@@ -471,24 +463,20 @@ def _launch(fp, p, data, stream, mode, nz_out=None):
         p.data_ptr(), p.shape[1], fp.rec.data_ptr(), fp.rec_start.data_ptr(),
         fp.st_fl0.data_ptr(), fp.fl.data_ptr(), fp.nst, fp.ntiles, fp.S, fp.T, fp.ring,
         fp.rec_cap, fp.vcap, fp.pool_cap, fp.ctas_per_sm, mode, C.c_double(fp.w), fp.nqp,
-        data.data_ptr(), fp.scratch.data_ptr(), fp.flag.data_ptr(), nz_out,
-        fp.sptr.data_ptr(), fp.gslot.data_ptr(), fp.gslot2.data_ptr(),
-        fp.cnt.data_ptr() if (fp.inkernel_combine and nz_out is None) else None, stream)
+        data.data_ptr(), fp.scratch.data_ptr(), fp.flag.data_ptr(), nz_out, stream)
     _lib.check(code, "skb_p1tet_laplace_fused2")
 
 
 def run(fp, data, stream, fast=False, p=None):
-    """Warm numeric phase: one kernel launch (two with ``fp.inkernel_combine = False``).  ``p``: vertex coordinates to
+    """Warm numeric phase: two kernel launches, nothing else.  ``p``: vertex coordinates to
     assemble with (default: the ones the plan was built from; same shape, same device; the
     caller vouches that they stay within the range ``fp.mode`` was chosen for, see
     :func:`arithmetic_mode`)."""
     lib = _lib.lib()
     _launch(fp, fp.p if p is None else p, data, stream, 3 if fast else fp.mode)
-    if not fp.inkernel_combine:      # second kernel: the shared slots' partials, in order
-        code = lib.skb_p1_combine2(fp.scratch.data_ptr(), fp.sptr.data_ptr(),
-                                   fp.gslot.data_ptr(), fp.gslot2.data_ptr(), fp.nshared,
-                                   data.data_ptr(), stream)
-        _lib.check(code, "skb_p1_combine2")
+    code = lib.skb_p1_combine2(fp.scratch.data_ptr(), fp.sptr.data_ptr(), fp.gslot.data_ptr(),
+                               fp.gslot2.data_ptr(), fp.nshared, data.data_ptr(), stream)
+    _lib.check(code, "skb_p1_combine2")
 
 
 def pattern_changed(fp, reset=True):
