@@ -208,6 +208,17 @@ int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
 int skb_p1_combine2(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
                     const uint32_t *gslot2, int64_t nshared, double *csr_data, void *stream);
 
+/* ---- multi-GPU interface rows: the device steps around the NCCL
+ * all-to-all-v that replaces PETSc's MATIS -> mpiaij row addition (coo_data.py:151-170).
+ * skb_pack_interface: out[i] = vals[slots[i]] (values of the CSR slots whose row a peer owns,
+ * destination-major).  skb_unpack_add_interface: data[pos[i]] += recv[i] for one received
+ * segment; targets within a segment are distinct and the caller issues the segments in
+ * source-rank order on one stream, so the sums are deterministic (no atomics).            */
+int skb_pack_interface(const double *vals, const int64_t *slots, int64_t n, double *out,
+                       void *stream);
+int skb_unpack_add_interface(double *data, const int64_t *pos, const double *recv, int64_t n,
+                             void *stream);
+
 /* ---- materialised basis for traced (user-defined) forms -----------------
  * grad: (dim, nel, nqp) of scalar basis function b (element_h1.py:17);
  * dx: (nel, nqp) (cell_basis.py:104-105); x: (dim, nel, nqp)

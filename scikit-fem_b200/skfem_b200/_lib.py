@@ -55,6 +55,8 @@ SIGNATURES = {
                                         _P, _P, _P]),
     "skb_p1_fused2_smem_bytes": (_I64, [_I32, _I32, _I32, _I32, _I32]),
     "skb_p1_combine2": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
+    "skb_pack_interface": (_INT, [_P, _P, _I64, _P, _P]),
+    "skb_unpack_add_interface": (_INT, [_P, _P, _P, _I64, _P]),
     "skb_debug_flags": (None, [_INT]),
     "skb_sm_reserve": (None, [_INT]),
     "skb_l2_window": (_INT, [_P, _I64, _P]),
@@ -95,6 +97,32 @@ def lib():
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+class nvtx:
+    """NVTX range around a seam of the pipeline (visible in nsys / ncu timelines); the
+    reference only logs at these seams (form.py:76,79; bilinear_form.py:145-147;
+    cell_basis.py:80,106).  A no-op where NVTX is unavailable."""
+
+    def __init__(self, name):
+        self.name = name
+        self.on = False
+
+    def __enter__(self):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.nvtx.range_push(self.name)
+                self.on = True
+        except Exception:
+            self.on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def check(code, what=""):

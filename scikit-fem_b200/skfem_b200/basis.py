@@ -209,7 +209,8 @@ class CellBasis(AbstractBasis):
         d = self._devcache.get(key)
         if d is not None:
             return d
-        p, t = self.mesh.device_arrays(device)
+        with _lib.nvtx("skfem_b200:basis-upload"):
+            p, t = self.mesh.device_arrays(device)
         d = {"device": device, "p": p, "t": t}
 
         def up(a, dtype=None):

@@ -81,6 +81,35 @@ def all_to_all_v(send, send_counts, recv_counts, group=None):
     return recv
 
 
+def _pack(vals, slots):
+    """vals[slots] - on CUDA through the library's pack kernel."""
+    if not vals.is_cuda:
+        return vals[slots]
+    import ctypes as C
+    torch = _torch()
+    from . import _lib as L
+    out = torch.empty(slots.shape[0], dtype=vals.dtype, device=vals.device)
+    L.check(_lib().skb_pack_interface(vals.data_ptr(), slots.data_ptr(), slots.shape[0],
+                                      out.data_ptr(),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+            "skb_pack_interface")
+    return out
+
+
+def _add_segment(data, pos, recv):
+    """data[pos] += recv for one source rank's segment (distinct targets)."""
+    if not data.is_cuda:
+        data.index_add_(0, pos, recv)
+        return
+    import ctypes as C
+    torch = _torch()
+    from . import _lib as L
+    L.check(_lib().skb_unpack_add_interface(data.data_ptr(), pos.data_ptr(), recv.data_ptr(),
+                                            pos.shape[0],
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+            "skb_unpack_add_interface")
+
+
 class InterfaceExchange:
     """Plan + numeric phase of the interface-row reduction for one local CSR
     pattern.  ``grow``/``gcol``: global row / column of every local CSR slot
@@ -95,63 +124,74 @@ class InterfaceExchange:
         self.ranges = np.asarray(ranges, dtype=np.int64)
         self.ncols = int(ncols)
         dev = grow.device
-        ends = torch.as_tensor(self.ranges[1:], device=dev)
-        owner = torch.searchsorted(ends, grow, right=True)
-        key = grow * self.ncols + gcol
-        # destination-major, key-sorted send order (deterministic)
-        order = torch.argsort(owner * (int(self.ranges[-1]) * self.ncols + 1) + key)
-        owner_s = owner[order]
-        counts = torch.bincount(owner_s, minlength=world)[:world]
-        self.send_counts = [int(c) for c in counts.cpu()]
-        self.send_order = order
-        # exchange counts, then keys
-        cnt_t = torch.as_tensor(self.send_counts, dtype=torch.int64, device=dev)
-        recv_cnt = all_to_all_v(cnt_t, [1] * world, [1] * world, group)
-        self.recv_counts = [int(c) for c in recv_cnt.cpu()]
-        recv_keys = all_to_all_v(key[order], self.send_counts, self.recv_counts, group)
-        # my final row block: sorted unique of everything addressed to me
-        final = torch.unique(recv_keys, sorted=True)
-        self.pos_recv = torch.searchsorted(final, recv_keys)
+        i64 = torch.int64
         r0, r1 = int(self.ranges[rank]), int(self.ranges[rank + 1])
+        nloc = int(grow.shape[0])
+        key = grow * self.ncols + gcol
+        mine = (grow >= r0) & (grow < r1)
+        own_slots = torch.nonzero(mine).flatten()
+        own_keys = key[own_slots]
+        if own_keys.numel() > 1 and not bool((own_keys[1:] > own_keys[:-1]).all()):
+            # l2g not monotone: sort once (the local CSR order is then not the global one)
+            own_keys, o = torch.sort(own_keys)
+            own_slots = own_slots[o]
+        # only slots whose row another rank owns travel: destination-major, key-sorted
+        rem_slots = torch.nonzero(~mine).flatten()
+        ends = torch.as_tensor(self.ranges[1:], device=dev)
+        rem_owner = torch.searchsorted(ends, grow[rem_slots], right=True)
+        rem_keys = key[rem_slots]
+        o = torch.argsort(rem_owner * (int(self.ranges[-1]) * self.ncols + 1) + rem_keys)
+        rem_slots, rem_keys, rem_owner = rem_slots[o], rem_keys[o], rem_owner[o]
+        cnt_t = torch.bincount(rem_owner, minlength=world)[:world].to(i64)
+        recv_cnt = all_to_all_v(cnt_t, [1] * world, [1] * world, group)
+        both = torch.stack([cnt_t, recv_cnt]).cpu()            # one synchronisation
+        self.send_counts_remote = [int(c) for c in both[0]]
+        self.recv_counts_remote = [int(c) for c in both[1]]
+        recv_keys = all_to_all_v(rem_keys, self.send_counts_remote, self.recv_counts_remote,
+                                 group)
+        # my final row block = own keys (sorted, unique) merged with the received keys that
+        # are new to me; no sort of the big array: new keys are few (one interface layer)
+        pos = torch.searchsorted(own_keys, recv_keys).clamp(max=max(int(own_keys.numel()) - 1, 0))
+        have = (own_keys[pos] == recv_keys) if own_keys.numel() else torch.zeros_like(
+            recv_keys, dtype=torch.bool)
+        new_keys = torch.unique(recv_keys[~have], sorted=True)
+        shift = torch.searchsorted(new_keys, own_keys)          # new keys below each own key
+        own_final = torch.arange(int(own_keys.numel()), device=dev, dtype=i64) + shift
+        new_final = torch.searchsorted(own_keys, new_keys) + torch.arange(
+            int(new_keys.numel()), device=dev, dtype=i64)
+        self.nnz = int(own_keys.numel() + new_keys.numel())
+        final = torch.empty(self.nnz, dtype=i64, device=dev)
+        final[own_final] = own_keys
+        final[new_final] = new_keys
+        self.pos_recv_remote = torch.where(
+            have, own_final[pos] if own_keys.numel() else pos,
+            new_final[torch.searchsorted(new_keys, recv_keys).clamp(
+                max=max(int(new_keys.numel()) - 1, 0))] if new_keys.numel() else pos)
         rows = final // self.ncols - r0
         self.nrows = r1 - r0
         self.row0 = r0
-        self.nnz = int(final.shape[0])
         self.indices = (final - (rows + r0) * self.ncols)
         rowcount = torch.bincount(rows, minlength=self.nrows)[:self.nrows]
-        self.indptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev),
+        self.indptr = torch.cat([torch.zeros(1, dtype=i64, device=dev),
                                  torch.cumsum(rowcount, 0)])
         # the block is handed out like scipy's own CSR: int32 pattern whenever it fits
         if self.nnz < 2 ** 31 and self.ncols < 2 ** 31:
             self.indices = self.indices.to(torch.int32)
             self.indptr = self.indptr.to(torch.int32)
-        self.ro = np.concatenate([[0], np.cumsum(self.recv_counts)]).astype(np.int64)
-        self.bytes_per_exchange = 8 * (sum(self.send_counts) - self.send_counts[rank])
+        self.ro_remote = np.concatenate([[0], np.cumsum(self.recv_counts_remote)]).astype(np.int64)
+        self.bytes_per_exchange = 8 * sum(self.send_counts_remote)
         # ---- direct-write layout for the fused kernel --------------------------------
         # The kernel can write every local CSR slot straight to its destination:
         # out = [ my final row block (nnz) | send buffer, destination-major ].
         # slot_map[local slot] = index in `out`.
-        so = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
-        nloc = int(key.shape[0])
-        a_self, b_self = int(so[rank]), int(so[rank + 1])
-        own_slots = order[a_self:b_self]
-        ra, rb = int(self.ro[rank]), int(self.ro[rank + 1])
-        slot_map = torch.empty(nloc, dtype=torch.int64, device=dev)
-        slot_map[own_slots] = self.pos_recv[ra:rb]               # own slots -> final positions
-        remote = torch.cat([order[:a_self], order[b_self:]])     # destination-major
-        self.nsend = int(remote.shape[0])
-        slot_map[remote] = self.nnz + torch.arange(self.nsend, device=dev)
+        self.own_slots, self.own_final, self.rem_slots = own_slots, own_final, rem_slots
+        slot_map = torch.empty(nloc, dtype=i64, device=dev)
+        slot_map[own_slots] = own_final
+        self.nsend = int(rem_slots.shape[0])
+        slot_map[rem_slots] = self.nnz + torch.arange(self.nsend, device=dev)
         self.slot_map = slot_map
-        self.send_counts_remote = list(self.send_counts)
-        self.send_counts_remote[rank] = 0
-        self.recv_counts_remote = list(self.recv_counts)
-        self.recv_counts_remote[rank] = 0
-        self.pos_recv_remote = torch.cat([self.pos_recv[:ra], self.pos_recv[rb:]])
-        self.ro_remote = np.concatenate([[0], np.cumsum(self.recv_counts_remote)]).astype(np.int64)
         # final slots nobody on this rank writes (received-only) must start at zero
-        written = torch.zeros(self.nnz, dtype=torch.bool, device=dev)
-        written[self.pos_recv[ra:rb]] = True
-        self.unwritten = torch.nonzero(~written).flatten()
+        self.unwritten = new_final
 
     def finish(self, out, zero=True):
         """Numeric phase when the kernel wrote `out` through ``slot_map``:
@@ -167,19 +207,22 @@ class InterfaceExchange:
             for src in range(self.world):
                 a, b = int(self.ro_remote[src]), int(self.ro_remote[src + 1])
                 if b > a:
-                    data.index_add_(0, self.pos_recv_remote[a:b], recv[a:b])
+                    _add_segment(data, self.pos_recv_remote[a:b], recv[a:b])
         return data
 
     def reduce(self, local_vals):
-        """Values of my row block from every rank's local values."""
+        """Values of my row block from every rank's local values: own slots first, then the
+        received segments in source-rank order (the same order as :meth:`finish`)."""
         torch = _torch()
-        packed = local_vals[self.send_order]                     # pack (gather)
-        recv = all_to_all_v(packed, self.send_counts, self.recv_counts, self.group)
         data = torch.zeros(self.nnz, dtype=local_vals.dtype, device=local_vals.device)
-        for src in range(self.world):                            # fixed order: deterministic
-            a, b = int(self.ro[src]), int(self.ro[src + 1])
-            if b > a:
-                data.index_add_(0, self.pos_recv[a:b], recv[a:b])  # distinct targets per source
+        data[self.own_final] = local_vals[self.own_slots]
+        if self.world > 1:
+            recv = all_to_all_v(_pack(local_vals, self.rem_slots), self.send_counts_remote,
+                                self.recv_counts_remote, self.group)
+            for src in range(self.world):                        # fixed order: deterministic
+                a, b = int(self.ro_remote[src]), int(self.ro_remote[src + 1])
+                if b > a:                                        # distinct targets per source
+                    _add_segment(data, self.pos_recv_remote[a:b], recv[a:b])
         return data
 
 

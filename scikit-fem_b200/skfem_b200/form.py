@@ -529,7 +529,9 @@ class BilinearForm(Form):
                         plan.nnz, dtype=torch.float64, device=fp.p.device)
                     if getattr(fp, "version", 1) == 2:
                         from . import fused2
-                        fused2.run(fp, data, _stream(), fast=_CONFIG["fused_arith"] == "fast")
+                        with _lib.nvtx("skfem_b200:fused"):
+                            fused2.run(fp, data, _stream(),
+                                       fast=_CONFIG["fused_arith"] == "fast")
                         # first run after basis.update_points: did the zero mask of any local
                         # matrix change?  Then this pattern is no longer the reference's.
                         if getattr(fp, "unchecked", False) and \
@@ -546,7 +548,8 @@ class BilinearForm(Form):
                         fused.run(fp, data, _stream(), fast=_CONFIG["fused_arith"] == "fast",
                                   l2_persist=bool(_CONFIG["fused_l2_persist"]))
                     return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
-        local = self._local(ubasis, vbasis, **kwargs)
+        with _lib.nvtx("skfem_b200:local"):
+            local = self._local(ubasis, vbasis, **kwargs)
         nz = None
         if plan is None and key is None:
             # traced form: the pattern is a function of (element_dofs, zero mask of the
@@ -556,8 +559,9 @@ class BilinearForm(Form):
         if plan is None:
             if out is not None:
                 raise ValueError("out= needs an existing plan: assemble once without it")
-            plan = build_plan(vb._dev()["edofs"], ubasis._dev()["edofs"], ubasis.nelems,
-                              (vb.N, ubasis.N), local, drop_zeros=True)
+            with _lib.nvtx("skfem_b200:plan"):
+                plan = build_plan(vb._dev()["edofs"], ubasis._dev()["edofs"], ubasis.nelems,
+                                  (vb.N, ubasis.N), local, drop_zeros=True)
             if key is not None:
                 ubasis._plans[key] = plan
             else:
@@ -576,7 +580,8 @@ class BilinearForm(Form):
     def assemble(self, ubasis, vbasis=None, **kwargs):
         """Assemble into ``scipy.sparse.csr_matrix`` (bilinear_form.py:130-148)."""
         logger.info("Assembling '{}'.".format(getattr(self.form, "__name__", "form")))
-        A = self.assemble_device(ubasis, vbasis, **kwargs).to_scipy()
+        with _lib.nvtx("skfem_b200:assemble"):
+            A = self.assemble_device(ubasis, vbasis, **kwargs).to_scipy()
         logger.info("Assembling finished.")
         return A
 
