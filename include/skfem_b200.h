@@ -226,6 +226,11 @@ int skb_unpack_add_interface(double *data, const int64_t *pos, const double *rec
  * detabs: (nel, nqp) |detDF|.  Any output pointer may be NULL.             */
 int skb_tabulate(const skb_space_t *space, int b, double *grad, double *dx, double *x,
                  double *detabs, void *stream);
+/* Mapping.DF / invDF / detDF (mapping/mapping.py:6-114; mapping_affine.py:205-232,
+ * mapping_isoparametric.py:173-226) at the space's quadrature points: DF, invDF
+ * (dim, dim, nel, nqp), det (nel, nqp) signed.  Any output pointer may be NULL.  Hexahedra:
+ * returns SKB_EZERODET like the reference raises (synchronises the stream).                 */
+int skb_mapping(const skb_space_t *space, double *DF, double *invDF, double *det, void *stream);
 /* out[e] = sum over q of integrand[e,q]*dx[e,q] (bilinear_form.py:150-151) in
  * numpy's order: pairwise (numpy pairwise_sum) when the product array is
  * C-ordered, plain left-to-right (sequential != 0) when it is Fortran-ordered

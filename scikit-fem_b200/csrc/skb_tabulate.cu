@@ -116,6 +116,73 @@ tabulate_hex_kernel(const skb_space_t s, int b, double *__restrict__ grad, doubl
   }
 }
 
+// Mapping.DF / invDF / detDF at the quadrature points (mapping/mapping.py:6-114): the arrays
+// of shape (dim, dim, nel, nqp) and (nel, nqp) the reference's Mapping classes return
+// (mapping_affine.py:205-232, mapping_isoparametric.py:173-226), signed determinant.
+template <int DIM>
+__global__ void __launch_bounds__(128)
+mapping_affine_kernel(const skb_space_t s, double *__restrict__ DF, double *__restrict__ invDF,
+                      double *__restrict__ det) {
+  const int nqp = s.nqp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < s.nel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t eg = s.tind ? (int64_t)s.tind[e] : e;
+    Affine<DIM> g;
+    affine_load<DIM>(g, s.p, s.npts, s.t, s.nel_total, eg);
+    affine_invert(g);
+    for (int q = 0; q < nqp; ++q) {
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) {
+          const int64_t o = (((int64_t)(i * DIM + j)) * s.nel + e) * nqp + q;
+          if (DF) DF[o] = g.A[i][j];
+          if (invDF) invDF[o] = g.inv[i][j];
+        }
+      if (det) det[e * nqp + q] = g.det;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+mapping_hex_kernel(const skb_space_t s, double *__restrict__ DF, double *__restrict__ invDF,
+                   double *__restrict__ detout, int *__restrict__ err) {
+  const int nqp = s.nqp;
+  const int64_t total = s.nel * nqp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / nqp;
+    const int q = (int)(idx - e * nqp);
+    const int64_t eg = s.tind ? (int64_t)s.tind[e] : e;
+    double J[3][3], nn[3][3], inv[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          const int32_t v = s.t[(int64_t)n * s.nel_total + eg];
+          acc = acc + s.p[(int64_t)i * s.npts + v] * __ldg(s.mdphi + (n * 3 + j) * nqp + q);
+        }
+        J[i][j] = acc;
+      }
+    const double det = det3(J);
+    if (det == 0.0) atomicExch(err, 1);
+    cofactors3(J, nn);
+    divide9(nn, det, inv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int64_t o = (((int64_t)(i * 3 + j)) * s.nel + e) * nqp + q;
+        if (DF) DF[o] = J[i][j];
+        if (invDF) invDF[o] = inv[i][j];
+      }
+    if (detout) detout[idx] = det;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 qp_reduce_kernel(const double *__restrict__ integrand, const double *__restrict__ dx, int64_t nel,
                  int nqp, int sequential, double *__restrict__ out) {
@@ -166,6 +233,42 @@ extern "C" int skb_tabulate(const skb_space_t *space, int b, double *grad, doubl
     SKB_CUDA_TRY(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     SKB_CUDA_TRY(cudaStreamSynchronize(st));
     SKB_CUDA_TRY(cudaFreeAsync(err, st));
+    if (herr) return SKB_EZERODET;
+    return (int)cudaGetLastError();
+  }
+  return SKB_EINVAL;
+}
+
+extern "C" int skb_mapping(const skb_space_t *space, double *DF, double *invDF, double *det,
+                           void *stream) {
+  using namespace skb;
+  if (!space) return SKB_EINVAL;
+  const skb_space_t s = *space;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s.nel == 0) return SKB_OK;
+  if (s.mapping == SKB_MAP_AFFINE) {
+    if (s.dim == 2)
+      mapping_affine_kernel<2><<<nblk(s.nel, 128), 128, 0, st>>>(s, DF, invDF, det);
+    else if (s.dim == 3)
+      mapping_affine_kernel<3><<<nblk(s.nel, 128), 128, 0, st>>>(s, DF, invDF, det);
+    else
+      return SKB_EINVAL;
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  if (s.mapping == SKB_MAP_ISO_HEX1) {
+    if (!s.mdphi) return SKB_EINVAL;
+    int *err = nullptr;
+    SKB_CUDA_TRY(cudaMallocAsync((void **)&err, sizeof(int), st));
+    SKB_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+    mapping_hex_kernel<<<nblk(s.nel * s.nqp, 128), 128, 0, st>>>(s, DF, invDF, det, err);
+    count_launch();
+    int herr = 0;
+    cudaError_t e1 = cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFreeAsync(err, st);
+    if (e1 != cudaSuccess) return (int)e1;
+    if (e2 != cudaSuccess) return (int)e2;
     if (herr) return SKB_EZERODET;
     return (int)cudaGetLastError();
   }

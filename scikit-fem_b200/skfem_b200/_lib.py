@@ -46,6 +46,7 @@ SIGNATURES = {
     "skb_csr_reduce": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "skb_vec_reduce": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "skb_tabulate": (_INT, [_SP, _INT, _P, _P, _P, _P, _P]),
+    "skb_mapping": (_INT, [_SP, _P, _P, _P, _P]),
     "skb_qp_reduce": (_INT, [_P, _P, _I64, _I32, _INT, _P, _P]),
     "skb_p1tet_laplace_fused": (_INT, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32,
                                        _I32, C.c_double, _I32, _P, _P, _P]),

@@ -63,6 +63,24 @@ class Element:
             n += self.edge_dofs * rd.nedges
         return int(n)
 
+    def gbasis(self, mapping, X, i, tind=None):
+        """Global basis function ``i`` at the local points ``X`` (dim, npts) of the elements
+        ``tind`` - the reference's ``Element.gbasis(mapping, X, i, tind)``
+        (element/element.py:67-99, element_h1.py:10-24, element_vector.py:36-48): a 1-tuple
+        holding a DiscreteField with ``value (nel, npts)`` and ``grad (dim, nel, npts)``
+        (vector elements: ``(dim, nel, npts)`` / ``(dim, dim, nel, npts)``), here resident on
+        the device (``.numpy()`` / ``np.asarray`` bring it to the host).  The push-forward runs
+        in ``skb_tabulate``; the ``(dim, dim, nel, npts)`` inverse Jacobians are never formed."""
+        from .basis import CellBasis
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise NotImplementedError("per-element local points are not supported")
+        if not 0 <= i < self.nbfun:
+            self._index_error()
+        b = CellBasis(mapping.mesh, self, mapping=mapping,
+                      quadrature=(X, np.ones(X.shape[1])), elements=tind, disable_doflocs=True)
+        return (b._basis_field_dev(i),)
+
     # -- host tables consumed by the kernels --------------------------------
     def tabulate(self, X):
         """(phi (nbs, nqp), dphi (nbs, dim, nqp)) of the *scalar* basis."""
@@ -262,9 +280,26 @@ def _lagrange2(node, x):
 class ElementHex2(ElementH1):
     """Triquadratic hexahedron (27 nodes: vertices, edge / facet / cell
     centres in RefHex order, cf. skfem/element/element_hex/element_hex2.py:
-    1213-1260).  The reference evaluates machine-generated Horner forms; this
-    tensor-product evaluation agrees to a few ulp (tests/test_host_api.py), not
-    bitwise - Hex2 parity is therefore value-level (rtol), see DESIGN.md."""
+    1213-1260).  The reference evaluates machine-generated Horner forms.  At the default
+    quadrature rule (7^3 Gauss points) ``tabulate`` returns the reference's own numbers from a
+    shipped constant table (data/hex2_tables.npz, tools/gen_hex2_tables.py); at
+    any other points the tensor-product evaluation below, which agrees with the reference to
+    a few ulp (tests/test_host_api.py), is used."""
+    _tables = None
+
+    def tabulate(self, X):
+        import os
+        if ElementHex2._tables is None:
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data",
+                                "hex2_tables.npz")
+            ElementHex2._tables = dict(np.load(path)) if os.path.exists(path) else {}
+        for key, Xt in ElementHex2._tables.items():
+            if key.startswith("X_") and Xt.shape == X.shape and np.array_equal(Xt, X):
+                order = key[2:]
+                return (ElementHex2._tables["phi_" + order].copy(),
+                        ElementHex2._tables["dphi_" + order].copy())
+        return super().tabulate(X)
+
     nodal_dofs = 1
     facet_dofs = 1
     edge_dofs = 1

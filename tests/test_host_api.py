@@ -55,14 +55,22 @@ def test_mesh_constructors_match_reference():
     assert np.array_equal(m.p, g["p"]) and np.array_equal(m.t, g["t"])
 
 
-def test_hex2_tables_close_to_reference():
+def test_hex2_tables_match_the_reference():
+    """At the default rule ElementHex2.tabulate returns the reference's own numbers (shipped
+    table) bit for bit; the tensor-product evaluation used at any other points
+    agrees with the reference's generated Horner forms to a few ulp."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "hex2_tables.npz"))
     e = fem.ElementHex2()
     X, W = fem.get_quadrature(e.refdom, 2 * e.maxdeg)
     assert np.array_equal(X, g["X"]) and np.array_equal(W, g["W"])
     phi, dphi = e.tabulate(X)
-    np.testing.assert_allclose(phi, g["phi"], rtol=0, atol=1e-14)
-    np.testing.assert_allclose(dphi, g["dphi"], rtol=0, atol=2e-14)
+    assert np.array_equal(phi, g["phi"]) and np.array_equal(dphi, g["dphi"])
+    phi_t, dphi_t = fem.element.Element.tabulate(e, X)              # tensor-product fallback
+    np.testing.assert_allclose(phi_t, g["phi"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(dphi_t, g["dphi"], rtol=0, atol=2e-14)
+    Xo = X[:, ::7] * 0.99                                           # not the shipped points
+    po, _ = e.tabulate(Xo)
+    np.testing.assert_allclose(po.sum(axis=0), 1.0, rtol=0, atol=1e-14)   # partition of unity
     b = fem.Basis(fem.MeshHex.init_tensor(*(3 * (np.linspace(0, 1, 3),))), e)
     gg = load("hex2_tensor2")
     assert np.array_equal(b.element_dofs, gg["element_dofs"]) and b.N == 125
