@@ -580,12 +580,160 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------
+# the other BASELINE configs (one GPU): --config p2 | c3 | c4
+# --------------------------------------------------------------------------
+CONFIGS = {
+    "p2": ("ElementTetP2 laplace on MeshTet.init_tensor {n}^3 pts (the metric's P2 case)", 61),
+    "c3": ("ElementVector(ElementTetP2) linear_elasticity(lame_parameters(1e3, 0.3)) on "
+           "MeshTet.init_tensor {n}^3 pts (BASELINE configs[2])", 70),
+    "c4": ("ElementHex2 laplace on MeshHex.init_tensor {n}^3 pts (BASELINE configs[3], FP64 "
+           "tensor-core Gram kernel)", 65),
+}
+
+
+def build_config(name, npts, pkg):
+    """(mesh, element, form) of a named config from package `pkg` (skfem_b200 or the
+    reference's skfem - same constructors, same names)."""
+    x = np.linspace(0, 1, npts)
+    if name == "p2":
+        from importlib import import_module
+        lap = import_module(pkg.__name__ + ".models.poisson").laplace
+        return pkg.MeshTet.init_tensor(x, x, x), pkg.ElementTetP2(), lap
+    if name == "c3":
+        from importlib import import_module
+        el = import_module(pkg.__name__ + ".models.elasticity")
+        return (pkg.MeshTet.init_tensor(x, x, x), pkg.ElementVector(pkg.ElementTetP2()),
+                el.linear_elasticity(*el.lame_parameters(1e3, 0.3)))
+    if name == "c4":
+        from importlib import import_module
+        lap = import_module(pkg.__name__ + ".models.poisson").laplace
+        return pkg.MeshHex.init_tensor(x, x, x), pkg.ElementHex2(), lap
+    raise ValueError(name)
+
+
+def run_config(args):
+    """Warm re-assembly of a named config through the generic path (element-local kernel ->
+    HBM -> deterministic segmented reduction over the cached plan); same JSON contract."""
+    import torch
+    torch.cuda.set_device(0)
+    import skfem_b200 as fem
+    from skfem_b200 import _lib
+    apply_options(args)
+    name = args.config
+    npts = args.cells + 1 if args.cells != 100 else CONFIGS[name][1]
+    m, elem, form = build_config(name, npts, fem)
+    basis = fem.Basis(m, elem)
+    nel = m.nelements
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    A = form.assemble_device(basis)
+    torch.cuda.synchronize()
+    cold_ms = 1e3 * (time.perf_counter() - t0)
+    nnz = A.nnz
+    out = torch.empty(nnz, dtype=torch.float64, device="cuda")
+
+    def step():
+        form.assemble_device(basis, out=out)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    _lib.lib().skb_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = int(_lib.lib().skb_launch_count(0))
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler.stop()
+    # size-independent checks: constants / rigid translations in the kernel, symmetry of the sums
+    S = torch.sparse_csr_tensor(A.indptr.long(), A.indices.long(), out, size=A.shape)
+    v = torch.zeros(basis.N, dtype=torch.float64, device="cuda")
+    v[::basis.ncomp] = 1.0
+    scale = float(out.abs().max())
+    checks = {"max_abs_A_times_constant_over_max_entry": float((S @ v).abs().max()) / scale,
+              "nnz": nnz}
+    if name == "c4":
+        checks["nnz_closed_form"] = (8 * (npts - 1) + 1) ** 3
+    checks["ok"] = bool(checks["max_abs_A_times_constant_over_max_entry"] < 1e-10 and
+                        checks.get("nnz_closed_form", nnz) == nnz)
+    nverts = m.p.shape[1]
+    nbs = basis.nbs
+    algo = (4 * m.t.shape[0] * nel + 8 * m.p.shape[0] * nverts + 8 * nnz +
+            (4 * nbs * nel if basis.element_dofs is not m.t else 0))
+    peak, peak_src = peaks()
+    achieved = algo / (ms_step * 1e-3) / 1e9
+    # CPU: the reference itself on a bounded chunk of the same mesh (CellBasis(elements=...))
+    cpu = None
+    if not args.no_cpu:
+        skfem = reference_package()
+        if skfem is not None:
+            mr, er, fr = build_config(name, npts, skfem)
+            chunk = np.arange(min(nel, {"p2": 200000, "c3": 8000, "c4": 1500}[name]))
+            t0 = time.perf_counter()
+            fr.assemble(skfem.Basis(mr, er, elements=chunk))
+            dt = time.perf_counter() - t0
+            cpu = {"value": len(chunk) / dt, "unit": "elements/s", "cores": 1,
+                   "kind": "reference",
+                   "sample": "the unmodified reference (oracle/_ref), single thread, "
+                             "Basis(elements=first {} elements) + assemble of the same mesh, "
+                             "{:.1f} s".format(len(chunk), dt)}
+    e2e = None
+    if not args.no_e2e and nnz < 2.5e8:
+        p_host, t_host = m.p, m.t
+
+        def e2e_step():
+            mm = type(m)(p_host, t_host)
+            return form.assemble(fem.Basis(mm, elem))
+        for _ in range(2):
+            Ah = e2e_step()
+        torch.cuda.synchronize()
+        k = 3
+        t0 = time.perf_counter()
+        for _ in range(k):
+            Ah = e2e_step()
+        dt = (time.perf_counter() - t0) / k
+        e2e = {"value": nel / dt, "unit": "elements/s",
+               "h2d_bytes_per_step": int(m.p.nbytes + m.t.nbytes),
+               "d2h_bytes_per_step": int(Ah.data.nbytes + Ah.indices.nbytes + Ah.indptr.nbytes),
+               "ms_per_step": 1e3 * dt,
+               "what": "cold: Mesh(p,t) + Basis (topology, DOF numbering) + form.assemble -> "
+                       "scipy csr_matrix, plan build included"}
+    line = {
+        "metric": "assembly elements/s (FP64, config {})".format(name), "value": nel / (ms_step * 1e-3),
+        "unit": "elements/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "nnz_per_s": nnz / (ms_step * 1e-3),
+        "config": {"workload": CONFIGS[name][0].format(n=npts) + ", warm re-assembly into CSR",
+                   "elements_per_gpu": nel, "dofs_per_gpu": basis.N, "nnz_per_gpu": nnz,
+                   "cold_plan_build_ms": cold_ms, "path": "generic",
+                   "l2": "no flush: local data and plan exceed the 126 MB L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": algo,
+                     "note": "compulsory bytes t + p + scalar element_dofs + CSR data (SURVEY "
+                             "8d); the generic path additionally writes and re-reads the "
+                             "element-local data"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checks": checks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "p2", "c3", "c4"],
+                    help="c2 (default): BASELINE configs[1], the headline; p2 / c3 / c4: the other "
+                         "single-GPU configs through the generic path (N=1 only)")
     ap.add_argument("--cells", type=int, default=100, help="cells per side (per GPU when weak)")
     ap.add_argument("--strong", action="store_true",
                     help="N>1: partition one global init_tensor mesh (cells per side) instead of "
@@ -647,6 +795,9 @@ def main():
         if int(os.environ.get("RANK", "0")) != 0:
             return
         run_reference(args)
+        return
+    if args.config != "c2":
+        run_config(args)
         return
     run_gpu(args)
 

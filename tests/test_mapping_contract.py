@@ -30,8 +30,9 @@ def test_mapping_arrays_match_the_reference():
     assert np.array_equal(mph.DF(Xh), g["hex_DF"])
     assert np.array_equal(mph.invDF(Xh), g["hex_invDF"])
     assert np.array_equal(mph.detDF(Xh), g["hex_detDF"])
+    flat = fem.MeshHex(0.0 * g["hex_p"], g["hex_t"])     # (the mapping holds its mesh weakly)
     with pytest.raises(Exception, match="Zero Jacobian determinant"):
-        fem.MeshHex(0.0 * g["hex_p"], g["hex_t"])._mapping().detDF(Xh)
+        flat._mapping().detDF(Xh)
 
 
 def test_element_gbasis_matches_the_reference():
