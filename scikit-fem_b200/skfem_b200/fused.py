@@ -76,7 +76,10 @@ def _kd_order(corner, T, order=None, seg_cnt=None):
     lo = corner.min(dim=1, keepdim=True).values
     hi = corner.max(dim=1, keepdim=True).values
     scale = float(2 ** 20 - 1)
-    q = ((corner - lo) / torch.clamp(hi - lo, min=1e-300) * scale).clamp(0, scale).to(i64)
+    # one scale for all axes: a split along the (physically) longest side of a box keeps the
+    # tiles compact also when the domain itself is a thin slab (multi-GPU parts)
+    span = torch.clamp((hi - lo).max(), min=1e-300)
+    q = ((corner - lo) / span * scale).clamp(0, scale).to(i64)
     if order is None:
         order = torch.arange(nel, device=dev, dtype=i64)
         seg_cnt = torch.tensor([nel], device=dev, dtype=i64)

@@ -137,8 +137,21 @@ def build(basis, plan, T=256, ring=3, pool_cap=2048, S=None, slot_map=None, spre
             raise FusedPlanTooBig("fused plan: a single tile needs more than {} accumulators"
                                   .format(pool_cap))
         S //= 2
+    # the kernel is latency bound: one more resident CTA per SM is worth more than a larger
+    # super-tile (fewer shared slots) - halve S while that buys a CTA
+    while fp.S > 1 and _ctas_per_sm(fp.smem) < 3:
+        fp2 = _build_with(basis, plan, T, ring, pool_cap, fp.S // 2, slot_map, spread, renumber,
+                          tl, p, corner, csr_key, mirror, n_canonical, arange, excl, dev,
+                          defer_finalize)
+        if fp2 is None or _ctas_per_sm(fp2.smem) <= _ctas_per_sm(fp.smem):
+            break
+        fp = fp2
     fp.ctas_per_sm = int(ctas_per_sm)
     return fp
+
+
+def _ctas_per_sm(smem):
+    return int((227 * 1024) // (smem + 1024))
 
 
 def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, tl, p, corner,
