@@ -127,7 +127,7 @@ __device__ __forceinline__ unsigned nonzero_bits(double v) {   // v != +-0, inte
 // The CTA processes the super-tiles blockIdx.x, blockIdx.x + gridDim.x, ...; its j-th tile
 // uses record buffer j % NR.
 // NT compute threads handle T / NT elements each (NT == T: one element per thread).
-template <int T, int MODE, int NT = T>
+template <int T, int MODE, int NT = T, bool PROF = false>
 __global__ void __launch_bounds__(NT + 32, (T >= 512 ? 2 : (T >= 256 ? 3 : 6)))
 p1tet_laplace_fused2_kernel(const P1v2Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -220,6 +220,19 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
   const double w1 = a.w;
   const double w4 = a.w * 4.0;
   unsigned bad = 0;
+  // PROF (skb_debug_flags bit 2, separate instantiation: the counters cost registers): lane 0
+  // of every warp of CTA 0 accumulates the cycles it spends per phase.  BAR.SYNC defers its
+  // blocking to the next memory instruction, hence the dummy shared-memory load.
+  const bool prof = PROF && blockIdx.x == 0 && lane == 0;
+  long long pc[PROF ? 6 : 1] = {0}, t0 = 0;
+#define SKB_TICK(i)                                  \
+  if (PROF && prof) {                                \
+    (void)*reinterpret_cast<volatile int *>(fl_np);  \
+    const long long t1_ = clock64();                 \
+    pc[PROF ? (i) : 0] += t1_ - t0;                  \
+    t0 = t1_;                                        \
+  }
+  if (PROF && prof) t0 = clock64();
   int slot = 0, par = 0;
   bool first_of_st = false;             // the first super-tile's flush table is already in flight
   // Invariant at the top of iteration `it`: the records of this tile and of the next one have
@@ -233,6 +246,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
     const bool last_of_st = tile + 1 >= tend;
     // the next tile's vertex coordinates travel while this tile is computed and reduced
     if (is_compute && has_next) gather(recs + (size_t)slot1 * a.rec_cap, par ^ 1);
+    SKB_TICK(0)
     // ---- P1: local matrix of element `tid` -> vals -------------------------------------
     if (is_compute && !(a.debug & 1)) {
 #pragma unroll 1
@@ -343,7 +357,9 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
       }
      }
     }
+    SKB_TICK(1)
     __syncthreads();   // (A) vals complete
+    SKB_TICK(2)
     if (is_producer) {
       // the record two tiles ahead must be visible at the top of the next iteration (its
       // vertex list feeds the gather); it has been in flight for NR - 2 iterations
@@ -413,8 +429,10 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
 #undef SKB_V
 #undef SKB_W
     }
+    SKB_TICK(3)
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // (B) vals, record `slot` free; coords of the next tile visible; pool updated
+    SKB_TICK(4)
     if (is_producer) issue_record();
     // ---- flush: the super-tile's pool -> csr_data / scratch, in CSR order --------------------
     if (last_of_st && is_compute && !(a.debug & 64)) {
@@ -431,6 +449,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
       }
       // the next super-tile's first pool write comes after barrier (A) of its first tile
     }
+    SKB_TICK(5)
     // next tile of the sequence
     first_of_st = last_of_st;
     if (last_of_st) {
@@ -444,6 +463,12 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
     par ^= 1;
   }
   if (bad & 0x3ffu) atomicOr(a.flag, 1);
+  if (PROF && prof)
+    printf("fused2 cta0 warp %d: tiles %d  cycles/tile: gather issue %lld  P1 %lld  "
+           "barrier A %lld  P2 %lld  cp.async wait + barrier B %lld  flush / record issue %lld\n",
+           warp, nmine, pc[0] / nmine, pc[PROF ? 1 : 0] / nmine, pc[PROF ? 2 : 0] / nmine,
+           pc[PROF ? 3 : 0] / nmine, pc[PROF ? 4 : 0] / nmine, pc[PROF ? 5 : 0] / nmine);
+#undef SKB_TICK
 }
 
 __global__ void __launch_bounds__(256)
@@ -461,10 +486,10 @@ p1_combine2_kernel(const double *__restrict__ scratch, const uint32_t *__restric
   }
 }
 
-template <int T, int MODE, int NT = T>
+template <int T, int MODE, int NT = T, bool PROF = false>
 static int launch_fused2(const P1v2Args &a, size_t smem, int sms, int ctas_per_sm,
                          cudaStream_t st) {
-  auto k = p1tet_laplace_fused2_kernel<T, MODE, NT>;
+  auto k = p1tet_laplace_fused2_kernel<T, MODE, NT, PROF>;
   SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   SKB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NT + 32, smem));
@@ -534,7 +559,9 @@ extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const voi
   }
   const int ept = ctas_per_sm >> 8;        // bits 8..: elements per compute thread (0/1 = one)
   ctas_per_sm &= 0xff;
-  if (ept <= 1) {
+  if ((a.debug & 4) && tile_elems == 256 && mode == 2 && ept <= 1) {
+    rc = launch_fused2<256, 2, 256, true>(a, smem, sms, ctas_per_sm, st);   // phase counters
+  } else if (ept <= 1) {
     SKB_P1V2_CASE(128)
     SKB_P1V2_CASE(256)
     SKB_P1V2_CASE(512)

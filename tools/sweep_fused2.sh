@@ -19,16 +19,16 @@ for l in sys.stdin:
         fp.get('per_element', 0)))
 " >> $out
 }
-while read -r line; do
-  [ -z "$line" ] && continue
-  run $line
-done <<'CFG'
+# configurations: the file given as $1, else the default list below
+cfg=${1:-}
+if [ -z "$cfg" ]; then
+  cfg=$(mktemp)
+  cat > $cfg <<'CFG'
 --tile2 256 --ring2 3 --pool 2048
 --tile2 256 --ring2 4 --pool 2048
 --tile2 256 --ring2 3 --pool 4096
 --tile2 512 --ring2 3 --pool 4096
 --tile2 512 --ring2 3 --pool 2048
---tile2 512 --ring2 4 --pool 4096
 --tile2 128 --ring2 3 --pool 2048
 --tile2 256 --ring2 3 --pool 2048 --debug-flags 1
 --tile2 256 --ring2 3 --pool 2048 --debug-flags 2
@@ -36,4 +36,10 @@ done <<'CFG'
 --tile2 256 --ring2 3 --pool 2048 --debug-flags 67
 --tile2 256 --ring2 3 --pool 2048 --arith fast
 CFG
+fi
+[ -r "$cfg" ] || { echo "no such configuration file: $cfg" >&2; exit 2; }
+while read -r line; do
+  [ -z "$line" ] && continue
+  run $line
+done < "$cfg"
 cat $out
