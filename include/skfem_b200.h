@@ -115,6 +115,35 @@ int skb_plan_finalize(int64_t ncoo, int64_t nrows, int64_t ncols, int64_t nnz, i
                       const uint64_t *keys_sorted, const uint32_t *vals_sorted, const uint32_t *slot,
                       int32_t *indptr, int32_t *indices, uint32_t *segptr, uint32_t *perm,
                       void *stream);
+/* The same plan without a global sort (csrc/skb_plan_rows.cu): row r only receives entries
+ * from the elements containing DOF r, so the triplets are bucketed by row (incidence lists
+ * built with integer atomics) and every row is sorted by (col, k) on its own in shared memory
+ * - one warp per row (in registers up to 128 surviving entries, in shared memory up to 512),
+ * one CTA per row up to 8192.  Outputs are bit for
+ * bit those of the two steps above.  Scratch (caller-provided, device): mask uint32[Nbv*nel],
+ * rc uint64[nrows], sums uint32[4096], incstart / candstart uint32[nrows+1], cursor
+ * uint32[2*nrows], nuniq uint32[nrows], inc_words uint32[2*counts[1]], dofs_ut int32[Nbu*nel],
+ * ucol / uoff uint32[counts[0]],
+ * flag int32[3].
+ * skb_plan_rows_count: counts_host[0] = nkeep, counts_host[1] = incidences kept (stream
+ * synchronised).  skb_plan_rows_sort: perm, indptr, *nnz_host (stream synchronised).
+ * skb_plan_rows_emit: indices, segptr.  SKB_ETOOBIG (Nbu > 32, a row with more than 8192
+ * entries, more than 2^24 rows ...): use the radix-sort path.                              */
+int skb_plan_rows_count(const int32_t *dofs_v, int32_t nbv, int32_t nbu, int64_t nel,
+                        int64_t nrows, const double *local_or_null, int drop_zeros,
+                        uint32_t *mask, unsigned long long *rc, uint32_t *sums,
+                        uint32_t *incstart, uint32_t *candstart, int64_t *counts_host,
+                        void *stream);
+int skb_plan_rows_sort(const int32_t *dofs_v, const int32_t *dofs_u, int32_t nbv, int32_t nbu,
+                       int64_t nel, int64_t nrows, const uint32_t *mask,
+                       const uint32_t *incstart, const uint32_t *candstart, uint32_t *cursor,
+                       uint32_t *inc_words, int32_t *dofs_ut, uint32_t *sums, uint32_t *perm,
+                       uint32_t *ucol,
+                       uint32_t *uoff, uint32_t *nuniq, int32_t *indptr, int32_t *flag,
+                       int64_t *nnz_host, void *stream);
+int skb_plan_rows_emit(int64_t nrows, int64_t nnz, int64_t nkeep, const uint32_t *candstart,
+                       const int32_t *indptr, const uint32_t *ucol, const uint32_t *uoff,
+                       int32_t *indices, uint32_t *segptr, void *stream);
 
 /* ---- numeric phase: replaces csr_sum_duplicates (coo_data.py:36) ----
  * data[s] = sum of local[perm[k]], k in [segptr[s], segptr[s+1]), added

@@ -16,6 +16,7 @@ SKB_MAP_AFFINE, SKB_MAP_ISO_HEX1 = 0, 1
 FORM_LAPLACE, FORM_MASS, FORM_VECTOR_LAPLACE, FORM_ELASTICITY = 0, 1, 2, 3
 LFORM_UNIT_LOAD = 0
 
+SKB_ETOOBIG = -2
 ERRORS = {-1: "SKB_EINVAL: bad argument / unsupported combination",
           -2: "SKB_ETOOBIG: tables do not fit on-chip or index overflow",
           -3: "Zero Jacobian determinant"}
@@ -43,6 +44,11 @@ SIGNATURES = {
                                  _P, _P, _P, _P, _P, _P, _I64, C.POINTER(_I64), _P]),
     "skb_plan_finalize": (_INT, [_I64, _I64, _I64, _I64, _I64, _P, _P, _P,
                                  _P, _P, _P, _P, _P]),
+    "skb_plan_rows_count": (_INT, [_P, _I32, _I32, _I64, _I64, _P, _INT, _P, _P, _P, _P, _P, _P,
+                                   _P]),
+    "skb_plan_rows_sort": (_INT, [_P, _P, _I32, _I32, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  _P, _P, _P, _P, _P, _P, _P]),
+    "skb_plan_rows_emit": (_INT, [_I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "skb_csr_reduce": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "skb_vec_reduce": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "skb_tabulate": (_INT, [_SP, _INT, _P, _P, _P, _P, _P]),

@@ -68,7 +68,7 @@ _CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring":
            "fused_arith": "exact", "fused_spread": True, "fused_renumber": True,
            "fused_l2_persist": True, "fused_tiling": "morton",
            "fused_version": 2, "fused2_tile": 256, "fused2_ring": 3, "fused2_pool": 2048,
-           "fused2_ctas": 0, "fused2_S": None, "fused2_ept": 1}
+           "fused2_ctas": 0, "fused2_S": None, "fused2_ept": 1, "plan_method": "rows"}
 
 
 def set_options(**kw):
@@ -201,8 +201,64 @@ def _mask_plan_put(ubasis, vbasis, nz, plan):
     del lst[:-MASK_PLANS_KEPT]
 
 
-def build_plan(dofs_v, dofs_u, nel, shape, local, drop_zeros=True):
-    """Sort/unique on the device (skb_plan_symbolic + skb_plan_finalize)."""
+def _build_plan_rows(plan, dofs_v, dofs_u, nel, nrows, local, drop_zeros):
+    """Row buckets + per-row sorts (csrc/skb_plan_rows.cu).  Returns False when a limit of
+    that path is hit (the caller then takes the radix-sort path)."""
+    torch = _torch()
+    lib = _lib.lib()
+    dev = dofs_v.device
+    nbv = dofs_v.shape[0]
+    nbu = 1 if dofs_u is None else dofs_u.shape[0]
+    i32, i64 = torch.int32, torch.int64
+
+    def u32(n):
+        return torch.empty(max(int(n), 1), dtype=i32, device=dev)
+    mask = u32(nbv * nel)
+    rc = torch.empty(nrows, dtype=i64, device=dev)
+    sums = u32(4096)
+    incstart, candstart = u32(nrows + 1), u32(nrows + 1)
+    counts = (C.c_int64 * 2)()
+    code = lib.skb_plan_rows_count(
+        dofs_v.data_ptr(), nbv, nbu, nel, nrows, None if local is None else local.data_ptr(),
+        1 if drop_zeros else 0, mask.data_ptr(), rc.data_ptr(), sums.data_ptr(),
+        incstart.data_ptr(), candstart.data_ptr(), counts, _stream())
+    if code == _lib.SKB_ETOOBIG:
+        return False
+    _lib.check(code, "skb_plan_rows_count")
+    nkeep, ninc = int(counts[0]), int(counts[1])
+    cursor, nuniq, inc = u32(2 * nrows), u32(nrows), u32(2 * ninc)
+    dofs_ut = u32(0 if dofs_u is None else nbu * nel)
+    perm, ucol, uoff = u32(nkeep), u32(nkeep), u32(nkeep)
+    indptr = torch.empty(nrows + 1, dtype=i32, device=dev)
+    flag = torch.empty(3, dtype=i32, device=dev)
+    nnz_c = C.c_int64(0)
+    code = lib.skb_plan_rows_sort(
+        dofs_v.data_ptr(), None if dofs_u is None else dofs_u.data_ptr(), nbv, nbu, nel, nrows,
+        mask.data_ptr(), incstart.data_ptr(), candstart.data_ptr(), cursor.data_ptr(),
+        inc.data_ptr(), dofs_ut.data_ptr(), sums.data_ptr(), perm.data_ptr(), ucol.data_ptr(),
+        uoff.data_ptr(),
+        nuniq.data_ptr(), indptr.data_ptr(), flag.data_ptr(), C.byref(nnz_c), _stream())
+    if code == _lib.SKB_ETOOBIG:
+        return False
+    _lib.check(code, "skb_plan_rows_sort")
+    nnz = int(nnz_c.value)
+    plan.nnz, plan.nkeep = nnz, nkeep
+    plan.indptr, plan.perm = indptr, perm
+    plan.indices = torch.empty(nnz, dtype=i32, device=dev)
+    plan.segptr = torch.empty(nnz + 1, dtype=i32, device=dev)
+    code = lib.skb_plan_rows_emit(nrows, nnz, nkeep, candstart.data_ptr(), indptr.data_ptr(),
+                                  ucol.data_ptr(), uoff.data_ptr(), plan.indices.data_ptr(),
+                                  plan.segptr.data_ptr(), _stream())
+    _lib.check(code, "skb_plan_rows_emit")
+    return True
+
+
+def build_plan(dofs_v, dofs_u, nel, shape, local, drop_zeros=True, method=None):
+    """The CSR structure + the per-slot lists of COO entries, built on the device:
+    ``method`` "rows" (default, ``set_options(plan_method=...)``): row buckets and per-row
+    sorts (skb_plan_rows_*); "sort": one global radix sort (skb_plan_symbolic +
+    skb_plan_finalize), also the fallback when a row is too long for the first.  Both give
+    the same arrays bit for bit."""
     torch = _torch()
     lib = _lib.lib()
     dev = dofs_v.device
@@ -220,6 +276,9 @@ def build_plan(dofs_v, dofs_u, nel, shape, local, drop_zeros=True):
         plan.indices = torch.zeros(0, dtype=i32, device=dev)
         plan.segptr = torch.zeros(1, dtype=i32, device=dev)
         plan.perm = torch.zeros(0, dtype=i32, device=dev)
+        return plan
+    if (method or _CONFIG["plan_method"]) == "rows" and \
+            _build_plan_rows(plan, dofs_v, dofs_u, nel, nrows, local, drop_zeros):
         return plan
     keys_a = torch.empty(ncoo, dtype=i64, device=dev)
     keys_b = torch.empty(ncoo, dtype=i64, device=dev)
