@@ -34,6 +34,28 @@ int debug_flags();
 // concurrent NCCL kernel when the interface exchange overlaps the next step
 int sm_reserve();
 
+// one device int, zeroed, released on every exit path (zero-determinant flag of the
+// isoparametric kernels)
+struct DeviceFlag {
+  int *p = nullptr;
+  cudaStream_t st;
+  explicit DeviceFlag(cudaStream_t s) : st(s) {}
+  cudaError_t init() {
+    cudaError_t e = cudaMallocAsync((void **)&p, sizeof(int), st);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    return cudaMemsetAsync(p, 0, sizeof(int), st);
+  }
+  // value after everything enqueued so far (synchronises the stream)
+  cudaError_t read(int *host) {
+    cudaError_t e = cudaMemcpyAsync(host, p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+  }
+  ~DeviceFlag() { if (p) cudaFreeAsync(p, st); }
+  DeviceFlag(const DeviceFlag &) = delete;
+  DeviceFlag &operator=(const DeviceFlag &) = delete;
+};
+
 // ---------------------------------------------------------------------------
 // Correctly rounded a/b for many numerators sharing one denominator.
 // y = RN(1/b) (__drcp_rn), q0 = RN(a*y), then Markstein corrections

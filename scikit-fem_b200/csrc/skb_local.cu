@@ -457,9 +457,9 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
     if (s.dim != 3 || s.nnodes != 8 || vec || !s.mdphi) return SKB_EINVAL;
     size_t smem = sizeof(double) * 10 * (size_t)s.nqp;
     if (smem > 200 * 1024) return SKB_ETOOBIG;
-    int *err = nullptr;
-    SKB_CUDA_TRY(cudaMallocAsync((void **)&err, sizeof(int), st));
-    SKB_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+    DeviceFlag flag(st);
+    SKB_CUDA_TRY(flag.init());
+    int *err = flag.p;
     if (BILINEAR && s.nbs > 8 && s.nbs <= 32 && (form == SKB_FORM_LAPLACE || form == SKB_FORM_MASS) &&
         !(debug_flags() & 8)) {
       // high-order hexes (value-level parity): Gram-matrix contraction on the FP64
@@ -476,9 +476,7 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
       count_launch();
     }
     int herr = 0;
-    SKB_CUDA_TRY(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SKB_CUDA_TRY(cudaStreamSynchronize(st));
-    SKB_CUDA_TRY(cudaFreeAsync(err, st));
+    SKB_CUDA_TRY(flag.read(&herr));
     if (herr) return SKB_EZERODET;
     return (int)cudaGetLastError();
   }

@@ -224,15 +224,13 @@ extern "C" int skb_tabulate(const skb_space_t *space, int b, double *grad, doubl
   }
   if (s.mapping == SKB_MAP_ISO_HEX1) {
     if (!s.mdphi || (x && !s.mphi)) return SKB_EINVAL;
-    int *err = nullptr;
-    SKB_CUDA_TRY(cudaMallocAsync((void **)&err, sizeof(int), st));
-    SKB_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+    DeviceFlag flag(st);
+    SKB_CUDA_TRY(flag.init());
+    int *err = flag.p;
     tabulate_hex_kernel<<<nblk(s.nel * s.nqp, 128), 128, 0, st>>>(s, b, grad, dx, x, detabs, err);
     count_launch();
     int herr = 0;
-    SKB_CUDA_TRY(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SKB_CUDA_TRY(cudaStreamSynchronize(st));
-    SKB_CUDA_TRY(cudaFreeAsync(err, st));
+    SKB_CUDA_TRY(flag.read(&herr));
     if (herr) return SKB_EZERODET;
     return (int)cudaGetLastError();
   }
@@ -258,17 +256,13 @@ extern "C" int skb_mapping(const skb_space_t *space, double *DF, double *invDF, 
   }
   if (s.mapping == SKB_MAP_ISO_HEX1) {
     if (!s.mdphi) return SKB_EINVAL;
-    int *err = nullptr;
-    SKB_CUDA_TRY(cudaMallocAsync((void **)&err, sizeof(int), st));
-    SKB_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+    DeviceFlag flag(st);
+    SKB_CUDA_TRY(flag.init());
+    int *err = flag.p;
     mapping_hex_kernel<<<nblk(s.nel * s.nqp, 128), 128, 0, st>>>(s, DF, invDF, det, err);
     count_launch();
     int herr = 0;
-    cudaError_t e1 = cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st);
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaFreeAsync(err, st);
-    if (e1 != cudaSuccess) return (int)e1;
-    if (e2 != cudaSuccess) return (int)e2;
+    SKB_CUDA_TRY(flag.read(&herr));
     if (herr) return SKB_EZERODET;
     return (int)cudaGetLastError();
   }

@@ -35,8 +35,8 @@ def _flatten_dofs(S, device):
     torch = _torch()
     if S is None:
         return None
-    if isinstance(S, dict):
-        return torch.cat([_flatten_dofs(v, device) for v in S.values()])
+    if isinstance(S, dict):     # np.unique(np.concatenate(...)): named sets may share DOFs
+        return torch.unique(torch.cat([_flatten_dofs(v, device) for v in S.values()]))
     if hasattr(S, "all") and not isinstance(S, np.ndarray) and not torch.is_tensor(S):
         S = S.all()
     if torch.is_tensor(S):

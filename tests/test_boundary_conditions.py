@@ -123,3 +123,27 @@ def test_gpu_ex01_on_device():
     x = fem.solve(*fem.condense(A, b, D=basis.get_dofs())).cpu().numpy()
     key = "x" if "x" in g.files else [k for k in g.files if g[k].shape == x.shape][0]
     np.testing.assert_allclose(x, g[key], rtol=0, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_gpu_condense_with_named_sets_sharing_dofs():
+    """D given as a dict of named sets that share corner DOFs is flattened with
+    np.unique(np.concatenate(...)) like the reference (utils.py:277-288)."""
+    import skfem_b200 as fem
+    from skfem_b200.models.poisson import laplace, unit_load
+    g = load("bc_tri_p1")
+    m = fem.MeshTri(g["p"], g["t"])
+    basis = fem.Basis(m, fem.ElementTriP1())
+    A, b = laplace.assemble_device(basis), unit_load.assemble_device(basis)
+    left = np.nonzero(m.p[0] == m.p[0].min())[0]
+    bottom = np.nonzero(m.p[1] == m.p[1].min())[0]
+    assert np.intersect1d(left, bottom).size > 0
+    both = np.unique(np.concatenate([left, bottom]))
+    A1, b1, x1, I1 = fem.condense(A, b, D={"left": left, "bottom": bottom})
+    A2, b2, x2, I2 = fem.condense(A, b, D=both)
+    S1, S2 = A1.to_scipy(), A2.to_scipy()
+    assert np.array_equal(S1.indptr, S2.indptr) and np.array_equal(S1.indices, S2.indices)
+    assert np.array_equal(S1.data, S2.data)
+    assert np.array_equal(b1.cpu().numpy(), b2.cpu().numpy())
+    assert np.array_equal(np.asarray(I1.cpu() if hasattr(I1, "cpu") else I1),
+                          np.asarray(I2.cpu() if hasattr(I2, "cpu") else I2))
