@@ -293,8 +293,9 @@ def run_gpu(args):
         x = np.linspace(0, 1, cells + 1)
         m = fem.MeshTet.init_tensor(x, x, x)
     else:
-        from skfem_b200.distributed import (DistributedAssembler, slab_mesh_tet, partition,
-                                            parity_check)
+        from skfem_b200.distributed import DistributedAssembler, slab_mesh_tet, partition
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from dist_parity import parity_check       # checker only (uses the oracle)
         # NCCL parity against the oracle at a size the oracle does in a second: every rank's
         # row block, eager / persistent-buffer / pipelined modes (printed as `parity`)
         if not args.no_check:

@@ -67,7 +67,7 @@ def _worker(rank, world, port, cxy, cz, out):
             for A in last:
                 assert torch.equal(A.data, A2.data), kw
         # the same check bench.py prints as `parity` at N > 1 (all modes, slab + partition)
-        from skfem_b200.distributed import parity_check
+        from dist_parity import parity_check
         par = parity_check(rank, world)
         assert par["ok"], par
         out[rank] = 1

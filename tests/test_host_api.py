@@ -272,3 +272,21 @@ def test_cell_basis_conveniences():
     assert b.zero_w().shape == (m.t.shape[1], len(b.W)) and sub.zero_w().shape[0] == sub.nelems
     with pytest.raises(NotImplementedError, match="Boundary of subdomain"):
         sub.boundary()
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """The oracle (and the reference copy under oracle/_ref) is test infrastructure: no file
+    of the product package may import, open or mention it."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "scikit-fem_b200")
+    pat = re.compile(r"\boracle\b|/root/reference|import\s+skfem\b|from\s+skfem\b")
+    hits = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(d, f), errors="replace") as fh:
+                    for n, line in enumerate(fh, 1):
+                        if pat.search(line):
+                            hits.append("{}:{}: {}".format(f, n, line.strip()))
+    assert not hits, hits
