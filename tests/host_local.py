@@ -49,6 +49,13 @@ DRIVERS = r"""
 extern "C" int host_local_affine(const skb_space_t *s, int form, double lambda, double two_mu,
                                  double *out, int bilinear, int cached) {
   const bool vec = s->ncomp > 1;
+  if (cached == 2) {     // register-cached symmetric kernel of scalar elements
+    if (vec || !bilinear) return -1;
+#define SYM(D, Q) if (s->dim == D && s->nqp == Q) { skb::local_affine_sym_kernel<D, Q>(*s, form, out); return 0; }
+    SYM(3, 4) SYM(3, 11) SYM(2, 3) SYM(2, 6)
+#undef SYM
+    return -1;
+  }
 #define CALL(D, V)                                                                     \
   do {                                                                                 \
     if (cached) skb::local_affine_cached_kernel<D, V>(*s, form, lambda, two_mu, out);  \
@@ -69,7 +76,7 @@ def _host_source():
     src = open(SRC).read()
     body = src.split('#include "skb_common.cuh"', 1)[1]
     # keep everything up to the block-cooperative hexahedral kernel
-    cut = body.index("template <bool BILINEAR>\n__global__ void __launch_bounds__(256)")
+    cut = body.index("__device__ __forceinline__ void hex_jacobian(")
     body = body[:cut].replace("extern __shared__ double smem[];", "double *smem = skb_host_smem;")
     open_ns = body.count("namespace skb {") - body.count("}  // namespace skb")
     return PRELUDE % {"hdr": HDR} + body + "}\n" * open_ns + DRIVERS
