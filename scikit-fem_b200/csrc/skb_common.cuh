@@ -238,6 +238,30 @@ __device__ double pw_sum(int n, F &f) {
   return ret;
 }
 
+// The same sum for a compile-time number of terms held in an array (registers): every loop
+// unrolls.  N <= 128 is one leaf of the recursion.
+template <int N>
+__device__ __forceinline__ double pw_sum_fixed(const double (&t)[N]) {
+  if (N < 8) {
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r = r + t[i];
+    return r;
+  }
+  static_assert(N <= 128, "one leaf of numpy's pairwise sum");
+  double r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = t[k < N ? k : 0];
+#pragma unroll
+  for (int i = 8; i < N - (N % 8); i += 8)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = r[k] + t[i + k < N ? i + k : 0];
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+  for (int i = N - (N % 8); i < N; ++i) res = res + t[i];
+  return res;
+}
+
 // Plain left-to-right sum.  numpy reduces this way when the (nel, nqp) operand
 // of np.sum(axis=1) is Fortran-ordered (the reduction axis is then the outer
 // loop): e.g. ``v * dx`` for an affine mesh, where dx = np.tile(detA, (nqp,1)).T

@@ -238,13 +238,16 @@ __device__ __forceinline__ double elasticity_sparse(int nu, int nv, const double
   return acc;
 }
 
-template <int DIM, bool VEC>
+// NQP > 0: the rule size is a compile-time constant - the gradient / dx arrays and the NQP
+// terms of an entry then live in registers and numpy's pairwise sum unrolls (pw_sum_fixed).
+template <int DIM, bool VEC, int NQP = 0>
 __global__ void __launch_bounds__(128)
 local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double two_mu,
                            double *__restrict__ out) {
   extern __shared__ double smem[];
   const Tables tab = stage_tables(smem, s);
-  const int nqp = s.nqp, nbs = s.nbs;
+  const int nqp = NQP ? NQP : s.nqp, nbs = s.nbs;
+  constexpr int MAXQ = NQP ? NQP : LOCAL_MAXQ;
   constexpr int NC = VEC ? DIM : 1;
   const int nb = nbs * NC;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < s.nel;
@@ -254,14 +257,19 @@ local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double 
     affine_load<DIM>(g, s.p, s.npts, s.t, s.nel_total, eg);
     affine_invert(g);
     const double absdet = fabs(g.det);
-    double gu[LOCAL_MAXQ][DIM], gv[LOCAL_MAXQ][DIM], dxq[LOCAL_MAXQ];
-    for (int q = 0; q < nqp; ++q) dxq[q] = absdet * tab.W[q];       // cell_basis.py:104-105
+    double gu[MAXQ][DIM], gv[MAXQ][DIM], dxq[MAXQ];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q)
+      if (q < nqp) dxq[q] = absdet * tab.W[q];                      // cell_basis.py:104-105
     for (int jb = 0; jb < nbs; ++jb) {
-      for (int q = 0; q < nqp; ++q) push_grad<DIM>(g.inv, tab.dphi + jb * DIM * nqp, nqp, q, gu[q]);
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q)
+        if (q < nqp) push_grad<DIM>(g.inv, tab.dphi + jb * DIM * nqp, nqp, q, gu[q]);
       const double *pj = tab.phi + jb * nqp;
       for (int ib = 0; ib < nbs; ++ib) {
-        for (int q = 0; q < nqp; ++q)
-          push_grad<DIM>(g.inv, tab.dphi + ib * DIM * nqp, nqp, q, gv[q]);
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q)
+          if (q < nqp) push_grad<DIM>(g.inv, tab.dphi + ib * DIM * nqp, nqp, q, gv[q]);
         const double *pi = tab.phi + ib * nqp;
         // nu, nv become compile-time constants after unrolling, which lets the
         // compiler keep only the structurally non-zero terms of the integrand
@@ -293,7 +301,16 @@ local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double 
               return val * dxq[q];              // bilinear_form.py:151
             };
             const int J = jb * NC + nu, I = ib * NC + nv;
-            out[((int64_t)J * nb + I) * s.nel + e] = pw_sum(nqp, f);
+            double r;
+            if (NQP) {
+              double term[MAXQ];
+#pragma unroll
+              for (int q = 0; q < MAXQ; ++q) term[q] = f(q);
+              r = pw_sum_fixed<MAXQ>(term);
+            } else {
+              r = pw_sum(nqp, f);
+            }
+            out[((int64_t)J * nb + I) * s.nel + e] = r;
           }
       }
     }
@@ -313,28 +330,6 @@ local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double 
 //    per pair.  P2 tetrahedra: 14.4 k instead of 40.7 k FP64 operations.
 // numpy's pairwise sum is replicated with compile-time loops (pw_sum_fixed).
 // ---------------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ double pw_sum_fixed(const double (&t)[N]) {
-  if (N < 8) {
-    double r = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r = r + t[i];
-    return r;
-  }
-  static_assert(N <= 128, "one leaf of numpy's pairwise sum");
-  double r[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) r[k] = t[k < N ? k : 0];
-#pragma unroll
-  for (int i = 8; i < N - (N % 8); i += 8)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = r[k] + t[i + k < N ? i + k : 0];
-  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-#pragma unroll
-  for (int i = N - (N % 8); i < N; ++i) res = res + t[i];
-  return res;
-}
-
 template <int DIM, int NQP>
 __global__ void __launch_bounds__(128)
 local_affine_sym_kernel(const skb_space_t s, int form, double *__restrict__ out) {
@@ -540,6 +535,23 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
     // other scalar cases: recomputing the push-forward per pair is cheaper than
     // the local-memory round trip (measured), so only vector elements - whose
     // dense integrand is 7x more FP64 work - take the cached/sparse kernel
+    if (BILINEAR && vec && !(debug_flags() & 8)) {
+#define SKB_LAUNCH_CACHED_FIXED(D, Q)                                                        \
+  if (s.dim == D && s.nqp == Q) {                                                            \
+    auto k = local_affine_cached_kernel<D, true, Q>;                                         \
+    if (smem > 48 * 1024)                                                                    \
+      SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        (int)smem));                                         \
+    k<<<grid, block, smem, st>>>(s, form, lambda, two_mu, out);                              \
+    count_launch();                                                                          \
+    return (int)cudaGetLastError();                                                          \
+  }
+      SKB_LAUNCH_CACHED_FIXED(3, 11)
+      SKB_LAUNCH_CACHED_FIXED(3, 4)
+      SKB_LAUNCH_CACHED_FIXED(2, 6)
+      SKB_LAUNCH_CACHED_FIXED(2, 3)
+#undef SKB_LAUNCH_CACHED_FIXED
+    }
     if (BILINEAR && vec && s.nqp <= LOCAL_MAXQ && !(debug_flags() & 8)) {
       if (s.dim == 2 && !vec) SKB_LAUNCH_CACHED(2, false);
       else if (s.dim == 2 && vec) SKB_LAUNCH_CACHED(2, true);

@@ -49,6 +49,13 @@ DRIVERS = r"""
 extern "C" int host_local_affine(const skb_space_t *s, int form, double lambda, double two_mu,
                                  double *out, int bilinear, int cached) {
   const bool vec = s->ncomp > 1;
+  if (cached == 3) {     // cached kernel of vector elements with a compile-time rule size
+    if (!vec || !bilinear) return -1;
+#define FIX(D, Q) if (s->dim == D && s->nqp == Q) { skb::local_affine_cached_kernel<D, true, Q>(*s, form, lambda, two_mu, out); return 0; }
+    FIX(3, 4) FIX(3, 11) FIX(2, 3) FIX(2, 6)
+#undef FIX
+    return -1;
+  }
   if (cached == 2) {     // register-cached symmetric kernel of scalar elements
     if (vec || !bilinear) return -1;
 #define SYM(D, Q) if (s->dim == D && s->nqp == Q) { skb::local_affine_sym_kernel<D, Q>(*s, form, out); return 0; }

@@ -53,8 +53,9 @@ def test_local_kernels_match_reference_bitwise(name):
             continue
         kid, _ = NATIVE[f]
         lam, two_mu = (LAME[0], 2. * LAME[1]) if f == "elasticity" else (1.0, 2.0)
-        # vector elements: dense and cached kernel; scalar: dense and register-cached symmetric
-        variants = [0, 1] if vector else [0, 2]
+        # vector elements: dense, cached and cached with a compile-time rule size; scalar: dense
+        # and register-cached symmetric
+        variants = [0, 1, 3] if vector else [0, 2]
         for cached in variants:
             out = np.full(nb * nb * nel, np.nan)
             rc = lib.host_local_affine(C.byref(sp), C.c_int(kid), C.c_double(lam),
