@@ -234,6 +234,16 @@ int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
                              int32_t pool_cap, int32_t ctas_per_sm, int32_t mode, double w,
                              int32_t nqp, double *csr_data, double *scratch, int32_t *flag,
                              uint16_t *nz_out, void *stream);
+/* The same pipeline for the mass form u * v (models/poisson.py:17-19) on ElementTetP1 with the
+ * 4-point rule: tab_host = phi[4][4] (basis function x quadrature point) followed by W[4]
+ * (host doubles).  Plan and records are built as for the Laplace form, from the mass matrix'
+ * own (full graph) pattern; entries follow numpy's order  sum_q (phi_j phi_i) * (|det| W_q). */
+int skb_p1tet_mass_fused2(const double *tab_host, const double *p, int64_t npts, const void *rec,
+                          const uint64_t *rec_start, const int64_t *st_fl0, const void *fl,
+                          int32_t nst, int32_t ntiles, int32_t tiles_per_super,
+                          int32_t tile_elems, int32_t ring, int32_t rec_cap, int32_t vcap,
+                          int32_t pool_cap, int32_t ctas_per_sm, double *csr_data,
+                          double *scratch, int32_t *flag, uint16_t *nz_out, void *stream);
 int skb_p1_combine2(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,
                     const uint32_t *gslot2, int64_t nshared, double *csr_data, void *stream);
 

@@ -56,6 +56,10 @@ struct P1v2Args {
   int32_t debug;
   int32_t *flag;                // device int: bit0 set when the zero mask of an element changed
   uint16_t *nz_out;             // plan time only: receives the zero mask of every element
+  // MODE 4 (mass): phi_j(x_q) * phi_i(x_q) for the 10 unique pairs (row-major upper triangle)
+  // at the 4 quadrature points, and the weights
+  double cq[10][4];
+  double wq[4];
 };
 
 struct RecHeader2 {             // 32 bytes at the start of every record
@@ -120,6 +124,8 @@ __device__ __forceinline__ unsigned nonzero_bits(double v) {   // v != +-0, inte
 //         ((v + v) + v) + v  (v = d * dx) equals 4 v = d * (4 dx) bit for bit - one
 //         multiplication instead of three operations (proof in DESIGN.md).
 // MODE 3: opt-in fast arithmetic (FMA + one reciprocal; values within a few ulp per term).
+// MODE 4: the mass form u * v (models/poisson.py:17-19) instead of the Laplace form: no inverse,
+//         entry = numpy's sum over the 4 points of (phi_j phi_i) * (|det| W_q).
 //
 // Roles: threads [0, T) compute (one element each in P1, the tile's slot groups in P2, the
 // flush), one more warp whose lane 0 is the producer: it waits for records / flush tables and
@@ -264,6 +270,28 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
           A[1][0] = c1[1] - y0; A[1][1] = c2[1] - y0; A[1][2] = c3[1] - y0;
           A[2][0] = c1[2] - z0; A[2][1] = c2[2] - z0; A[2][2] = c3[2] - z0;
         }
+        if (MODE == 4) {
+          // |det A| only (mapping_affine.py:92-98); phi_j * phi_i is element independent
+          const double m0 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+          const double m1 = A[1][0] * A[2][2] - A[1][2] * A[2][0];
+          const double m2 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+          const double adet = fabs(A[0][0] * m0 - A[0][1] * m1 + A[0][2] * m2);
+          double dxq[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dxq[q] = adet * a.wq[q];       // cell_basis.py:104-105
+          unsigned nz = 0;
+          double *out = vals + el;
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+            double val = 0.0;                                        // np.sum, n < 8: left to right
+#pragma unroll
+            for (int q = 0; q < 4; ++q) val = val + a.cq[k][q] * dxq[q];
+            nz |= nonzero_bits(val) << k;
+            out[k * T] = val;
+          }
+          bad |= (nz ^ keep);
+          if (a.nz_out) a.nz_out[(size_t)tile * T + el] = (uint16_t)nz;
+        } else {
         double det, n[3][3], inv[3][3];
         if (MODE == 3) {
 #pragma unroll
@@ -354,6 +382,7 @@ p1tet_laplace_fused2_kernel(const P1v2Args a) {
           }
         bad |= (nz ^ keep);
         if (a.nz_out) a.nz_out[(size_t)tile * T + el] = (uint16_t)nz;
+        }
       }
      }
     }
@@ -519,7 +548,7 @@ extern "C" int64_t skb_p1_fused2_smem_bytes(int32_t tile_elems, int32_t ring, in
 // reference's pattern and the caller must re-plan (coo_data.py:35, eliminate_zeros).
 // nz_out != NULL (plan time): only the local matrices are formed and the 10-bit zero mask of
 // element e of tile t is stored at nz_out[t * tile_elems + e]; nothing else is written.
-extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
+static int p1tet_fused2_launch(const double *tab_host, const double *p, int64_t npts, const void *rec,
                                         const uint64_t *rec_start, const int64_t *st_fl0,
                                         const void *fl, int32_t nst, int32_t ntiles,
                                         int32_t tiles_per_super, int32_t tile_elems,
@@ -533,7 +562,9 @@ extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const voi
       rec_cap <= 0 || (rec_cap & 15) || ring < 3 || ring > 8 || !flag || tiles_per_super < 1 ||
       ntiles > (int64_t)nst * tiles_per_super || ntiles <= (int64_t)(nst - 1) * tiles_per_super)
     return SKB_EINVAL;
-  if (mode < 0 || mode > 3 || ((mode == 1 || mode == 2) && nqp != 4)) return SKB_EINVAL;
+  if (mode < 0 || mode > 4 || ((mode == 1 || mode == 2 || mode == 4) && nqp != 4) ||
+      (mode == 4 && !tab_host))
+    return SKB_EINVAL;
   if (nst == 0) return SKB_OK;
   P1v2Args a;
   a.p = p; a.npts = npts; a.rec = (const unsigned char *)rec; a.rec_start = rec_start;
@@ -542,6 +573,18 @@ extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const voi
   a.rec_cap = rec_cap; a.vcap = vcap; a.pool_cap = pool_cap; a.ring = ring;
   a.csr_data = csr_data; a.scratch = scratch; a.w = w; a.nqp = nqp;
   a.debug = debug_flags(); a.flag = flag; a.nz_out = nz_out;
+  for (int k = 0; k < 10; ++k)
+    for (int q = 0; q < 4; ++q) a.cq[k][q] = 0.0;
+  for (int q = 0; q < 4; ++q) a.wq[q] = 0.0;
+  if (mode == 4) {
+    // phi (4 basis functions x 4 points), then W (4): the products phi_j * phi_i are rounded
+    // here exactly as numpy rounds u * v (bilinear_form.py:151 multiplies by dx afterwards)
+    int k = 0;
+    for (int i = 0; i < 4; ++i)
+      for (int j = i; j < 4; ++j, ++k)
+        for (int q = 0; q < 4; ++q) a.cq[k][q] = tab_host[j * 4 + q] * tab_host[i * 4 + q];
+    for (int q = 0; q < 4; ++q) a.wq[q] = tab_host[16 + q];
+  }
   if (nz_out) a.debug |= 2 | 64;     // plan-time mask pass: local matrices only
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;
@@ -555,7 +598,8 @@ extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const voi
     if (mode == 0) rc = launch_fused2<TT, 0>(a, smem, sms, ctas_per_sm, st);             \
     else if (mode == 1) rc = launch_fused2<TT, 1>(a, smem, sms, ctas_per_sm, st);        \
     else if (mode == 2) rc = launch_fused2<TT, 2>(a, smem, sms, ctas_per_sm, st);        \
-    else rc = launch_fused2<TT, 3>(a, smem, sms, ctas_per_sm, st);                       \
+    else if (mode == 3) rc = launch_fused2<TT, 3>(a, smem, sms, ctas_per_sm, st);        \
+    else rc = launch_fused2<TT, 4>(a, smem, sms, ctas_per_sm, st);                       \
   }
   const int ept = ctas_per_sm >> 8;        // bits 8..: elements per compute thread (0/1 = one)
   ctas_per_sm &= 0xff;
@@ -569,11 +613,44 @@ extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const voi
     if (mode == 0) rc = launch_fused2<512, 0, 256>(a, smem, sms, ctas_per_sm, st);
     else if (mode == 1) rc = launch_fused2<512, 1, 256>(a, smem, sms, ctas_per_sm, st);
     else if (mode == 2) rc = launch_fused2<512, 2, 256>(a, smem, sms, ctas_per_sm, st);
-    else rc = launch_fused2<512, 3, 256>(a, smem, sms, ctas_per_sm, st);
+    else if (mode == 3) rc = launch_fused2<512, 3, 256>(a, smem, sms, ctas_per_sm, st);
   }
 #undef SKB_P1V2_CASE
   if (rc == SKB_OK) count_launch();
   return rc;
+}
+
+
+extern "C" int skb_p1tet_laplace_fused2(const double *p, int64_t npts, const void *rec,
+                                        const uint64_t *rec_start, const int64_t *st_fl0,
+                                        const void *fl, int32_t nst, int32_t ntiles,
+                                        int32_t tiles_per_super, int32_t tile_elems,
+                                        int32_t ring, int32_t rec_cap,
+                                        int32_t vcap, int32_t pool_cap, int32_t ctas_per_sm,
+                                        int32_t mode, double w, int32_t nqp, double *csr_data,
+                                        double *scratch, int32_t *flag, uint16_t *nz_out,
+                                        void *stream) {
+  if (mode == 4) return SKB_EINVAL;
+  return p1tet_fused2_launch(nullptr, p, npts, rec, rec_start, st_fl0, fl, nst, ntiles,
+                             tiles_per_super, tile_elems, ring, rec_cap, vcap, pool_cap,
+                             ctas_per_sm, mode, w, nqp, csr_data, scratch, flag, nz_out, stream);
+}
+
+// The same pipeline for the mass form u * v on ElementTetP1 with the 4-point rule
+// (models/poisson.py:17-19): tab_host = phi[4][4] (basis function x quadrature point) followed
+// by W[4], host doubles.  The mass matrix has the full graph pattern; plan and records are built
+// exactly as for the Laplace form.
+extern "C" int skb_p1tet_mass_fused2(const double *tab_host, const double *p, int64_t npts,
+                                     const void *rec, const uint64_t *rec_start,
+                                     const int64_t *st_fl0, const void *fl, int32_t nst,
+                                     int32_t ntiles, int32_t tiles_per_super, int32_t tile_elems,
+                                     int32_t ring, int32_t rec_cap, int32_t vcap,
+                                     int32_t pool_cap, int32_t ctas_per_sm, double *csr_data,
+                                     double *scratch, int32_t *flag, uint16_t *nz_out,
+                                     void *stream) {
+  return p1tet_fused2_launch(tab_host, p, npts, rec, rec_start, st_fl0, fl, nst, ntiles,
+                             tiles_per_super, tile_elems, ring, rec_cap, vcap, pool_cap,
+                             ctas_per_sm, 4, 1.0, 4, csr_data, scratch, flag, nz_out, stream);
 }
 
 extern "C" int skb_p1_combine2(const double *scratch, const uint32_t *sptr, const uint32_t *gslot,

@@ -60,6 +60,8 @@ SIGNATURES = {
     "skb_p1tet_laplace_fused2": (_INT, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32,
                                         _I32, _I32, _I32, _I32, _I32, C.c_double, _I32, _P, _P,
                                         _P, _P, _P]),
+    "skb_p1tet_mass_fused2": (_INT, [_P, _P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32,
+                                     _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "skb_p1_fused2_smem_bytes": (_I64, [_I32, _I32, _I32, _I32, _I32]),
     "skb_p1_combine2": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "skb_pack_interface": (_INT, [_P, _P, _I64, _P, _P]),

@@ -285,7 +285,8 @@ class CellBasis(AbstractBasis):
         keep = {k: v for k, v in self._plans.items() if k in ("linear", "by-mask")}
         for k, fp in self._plans.items():
             if isinstance(k, tuple) and k and k[0] == "fused" and getattr(fp, "version", 1) == 2:
-                fp.mode = fused2.arithmetic_mode(d["p"], fp.w, fp.nqp)
+                if fp.mode != 4:            # (4: the mass form has one arithmetic variant)
+                    fp.mode = fused2.arithmetic_mode(d["p"], fp.w, fp.nqp)
                 fp.p = d["p"]
                 fp.unchecked = True
                 keep[k] = fp

@@ -560,7 +560,7 @@ class BilinearForm(Form):
         if (plan is not None and vbasis is None and not kwargs and use_fused()
                 and ubasis.nelems > 0 and plan.nnz > 0):
             from . import fused
-            if fused.applicable(ubasis, self):
+            if fused.applicable(ubasis, self, version=int(_CONFIG["fused_version"])):
                 fkey = ("fused", key) if slot_map is None else ("fused-mapped", key,
                                                                 id(slot_map))
                 fp = ubasis._plans.get(fkey, False)
@@ -573,7 +573,8 @@ class BilinearForm(Form):
                                            spread=bool(_CONFIG["fused_spread"]),
                                            renumber=bool(_CONFIG["fused_renumber"]),
                                            ctas_per_sm=int(_CONFIG["fused2_ctas"]) |
-                                           (int(_CONFIG["fused2_ept"]) << 8))
+                                           (int(_CONFIG["fused2_ept"]) << 8),
+                                           form_id=self.native[1])
                     ubasis._plans[fkey] = fp
                 if fp is False:
                     fp = fused.build_auto(ubasis, plan, T=fused_tile(),

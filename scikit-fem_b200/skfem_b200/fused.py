@@ -118,16 +118,22 @@ class P1FusedPlan:
     pass
 
 
-def applicable(basis, form):
+def applicable(basis, form, version=1):
+    """laplace on ElementTetP1 with an equal-weight rule; the second-generation kernel also
+    takes mass (u * v) with the 4-point rule."""
     from .element import ElementTetP1
-    if form.native is None or form.native[1] != _lib.FORM_LAPLACE:
+    if form.native is None or form.native[0] != "bilinear" or form.native[3] != "scalar":
         return False
     if not getattr(basis, "_native_ok", True):
         return False
     if not isinstance(basis.elem, ElementTetP1) or not basis._affine:
         return False
     W = basis.W
-    return bool(np.all(W == W[0]))
+    if form.native[1] == _lib.FORM_LAPLACE:
+        return bool(np.all(W == W[0]))
+    if form.native[1] == _lib.FORM_MASS:
+        return version == 2 and int(basis.nqp) == 4
+    return False
 
 
 def build(basis, plan, T=512, threads=480, ring=4, slot_map=None, spread=True, renumber=True,

@@ -76,7 +76,7 @@ class P1FusedPlan2:
 
 def applicable(basis, form):
     from .fused import applicable as _a
-    return _a(basis, form)
+    return _a(basis, form, version=2)
 
 
 def _pick_S(n_canonical, nel, T, pool_cap):
@@ -90,7 +90,7 @@ def _pick_S(n_canonical, nel, T, pool_cap):
 
 
 def build(basis, plan, T=256, ring=3, pool_cap=2048, S=None, slot_map=None, spread=True,
-          renumber=True, ctas_per_sm=0, defer_finalize=False):
+          renumber=True, ctas_per_sm=0, defer_finalize=False, form_id=None):
     """``slot_map`` (optional int64 tensor, CSR slot -> output index): targets written by
     the kernels are remapped through it (multi-GPU direct write).  ``pool_cap``: most
     accumulators a super-tile may need (shared memory: 8 B each); ``S``: tiles per
@@ -130,7 +130,8 @@ def build(basis, plan, T=256, ring=3, pool_cap=2048, S=None, slot_map=None, spre
         S = _pick_S(n_canonical, nel, T, pool_cap)
     while True:
         fp = _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, tl, p,
-                         corner, csr_key, mirror, n_canonical, arange, excl, dev, defer_finalize)
+                         corner, csr_key, mirror, n_canonical, arange, excl, dev, defer_finalize,
+                         form_id)
         if fp is not None:
             break
         if S == 1:
@@ -142,7 +143,7 @@ def build(basis, plan, T=256, ring=3, pool_cap=2048, S=None, slot_map=None, spre
     while fp.S > 1 and _ctas_per_sm(fp.smem) < 3:
         fp2 = _build_with(basis, plan, T, ring, pool_cap, fp.S // 2, slot_map, spread, renumber,
                           tl, p, corner, csr_key, mirror, n_canonical, arange, excl, dev,
-                          defer_finalize)
+                          defer_finalize, form_id)
         if fp2 is None or _ctas_per_sm(fp2.smem) <= _ctas_per_sm(fp.smem):
             break
         fp = fp2
@@ -155,7 +156,7 @@ def _ctas_per_sm(smem):
 
 
 def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, tl, p, corner,
-                csr_key, mirror, n_canonical, arange, excl, dev, defer_finalize):
+                csr_key, mirror, n_canonical, arange, excl, dev, defer_finalize, form_id=None):
     torch = _torch()
     i64 = torch.int64
     nel = int(tl.shape[1])
@@ -386,7 +387,16 @@ def _build_with(basis, plan, T, ring, pool_cap, S, slot_map, spread, renumber, t
     fp.p = p
     fp.ctas_per_sm = 0
     fp.flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    fp.mode = arithmetic_mode(p, fp.w, fp.nqp)
+    fp.form_id = _lib.FORM_LAPLACE if form_id is None else int(form_id)
+    if fp.form_id == _lib.FORM_MASS:
+        # phi[4][4] (basis function x quadrature point) then W[4], host doubles
+        fp.tab = (C.c_double * 20)(*np.concatenate(
+            [np.asarray(basis._phi, dtype=np.float64).reshape(-1)[:16],
+             np.asarray(basis.W, dtype=np.float64)[:4]]))
+        fp.mode = 4
+    else:
+        fp.tab = None
+        fp.mode = arithmetic_mode(p, fp.w, fp.nqp)
     fp.smem = int(_lib.lib().skb_p1_fused2_smem_bytes(T, ring, fp.rec_cap, fp.vcap, fp.pool_cap))
     if fp.smem > 227 * 1024:
         raise FusedPlanTooBig("fused plan: tile does not fit in shared memory "
@@ -457,7 +467,7 @@ def arithmetic_mode(p, w, nqp):
 
 
 def build_auto(basis, plan, T=256, ring=3, pool_cap=2048, S=None, slot_map=None, spread=True,
-               renumber=True, ctas_per_sm=0):
+               renumber=True, ctas_per_sm=0, form_id=None):
     """Build with the requested tile, halving it while it does not fit in shared memory
     (irregular meshes whose tiles touch many vertices).  Returns None if even the smallest
     tile is too big: the caller then stays on the generic path."""
@@ -465,13 +475,21 @@ def build_auto(basis, plan, T=256, ring=3, pool_cap=2048, S=None, slot_map=None,
         try:
             return build(basis, plan, T=tile, ring=ring, pool_cap=pool_cap, S=S,
                          slot_map=slot_map, spread=spread, renumber=renumber,
-                         ctas_per_sm=ctas_per_sm)
+                         ctas_per_sm=ctas_per_sm, form_id=form_id)
         except FusedPlanTooBig:
             continue
     return None
 
 
 def _launch(fp, p, data, stream, mode, nz_out=None):
+    if getattr(fp, "form_id", _lib.FORM_LAPLACE) == _lib.FORM_MASS:
+        code = _lib.lib().skb_p1tet_mass_fused2(
+            fp.tab, p.data_ptr(), p.shape[1], fp.rec.data_ptr(), fp.rec_start.data_ptr(),
+            fp.st_fl0.data_ptr(), fp.fl.data_ptr(), fp.nst, fp.ntiles, fp.S, fp.T, fp.ring,
+            fp.rec_cap, fp.vcap, fp.pool_cap, fp.ctas_per_sm & 0xff, data.data_ptr(),
+            fp.scratch.data_ptr(), fp.flag.data_ptr(), nz_out, stream)
+        _lib.check(code, "skb_p1tet_mass_fused2")
+        return
     code = _lib.lib().skb_p1tet_laplace_fused2(
         p.data_ptr(), p.shape[1], fp.rec.data_ptr(), fp.rec_start.data_ptr(),
         fp.st_fl0.data_ptr(), fp.fl.data_ptr(), fp.nst, fp.ntiles, fp.S, fp.T, fp.ring,
@@ -486,7 +504,8 @@ def run(fp, data, stream, fast=False, p=None):
     caller vouches that they stay within the range ``fp.mode`` was chosen for, see
     :func:`arithmetic_mode`)."""
     lib = _lib.lib()
-    _launch(fp, fp.p if p is None else p, data, stream, 3 if fast else fp.mode)
+    mass = getattr(fp, "form_id", _lib.FORM_LAPLACE) == _lib.FORM_MASS
+    _launch(fp, fp.p if p is None else p, data, stream, 3 if (fast and not mass) else fp.mode)
     code = lib.skb_p1_combine2(fp.scratch.data_ptr(), fp.sptr.data_ptr(), fp.gslot.data_ptr(),
                                fp.gslot2.data_ptr(), fp.nshared, data.data_ptr(), stream)
     _lib.check(code, "skb_p1_combine2")

@@ -176,6 +176,55 @@ def test_update_points_revalidates_the_pattern(options):
         laplace.assemble_device(b, out=out)
 
 
+def test_fused2_mass_form(options):
+    """The fused path also takes the mass form u * v on ElementTetP1 (4-point rule): golden
+    vectors of the real reference, the oracle on an unstructured mesh with several
+    super-tiles, bit-identical repeats, re-assembly on moved points."""
+    from oracle import skfem_oracle as O
+    from skfem_b200.models.poisson import mass
+    options(fused=True, fused_version=2, fused2_tile=128, fused2_pool=2048)
+
+    def plan_of(b):
+        fp = b._plans[("fused", mass._plan_key(b, None, {}))]
+        assert fp is not None and fp.version == 2 and fp.mode == 4
+        return fp
+    for name in ["tet_p1_tensor6", "tet_p1_ball2", "tet_p1_morphed5", "tet_p1_tensor_nonuniform"]:
+        g = load(name)
+        b = fem.Basis(mesh_from(g, "tet"), fem.ElementTetP1())
+        A0 = mass.assemble(b)                         # cold, generic path
+        A1 = mass.assemble(b)                         # warm, fused path
+        plan_of(b)
+        A2 = mass.assemble(b)
+        assert np.array_equal(A1.indptr, g["mass_indptr"])
+        assert np.array_equal(A1.indices, g["mass_indices"])
+        ref = g["mass_data"]
+        np.testing.assert_allclose(A1.data, ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
+        assert np.array_equal(A1.data, A2.data)
+        np.testing.assert_allclose(A1.data, A0.data, rtol=RTOL, atol=RTOL * np.abs(A0.data).max())
+    rng = np.random.default_rng(5)
+    x = np.sort(rng.random(17)); y = np.sort(rng.random(15)); z = np.sort(rng.random(16))
+    m = fem.MeshTet.init_tensor(x, y, z)
+    p0 = m.p + 0.002 * rng.standard_normal(m.p.shape)
+    m = fem.MeshTet(p0, m.t)
+    b = fem.Basis(m, fem.ElementTetP1())
+    mass.assemble(b)
+    A = mass.assemble(b)
+    fp = plan_of(b)
+    assert fp.nst > 1
+
+    def oracle(p):
+        return O.assemble_bilinear(O.mass, O.cell_basis(mesh_of(dict(p=p, t=m.t), "tet"),
+                                                        O.element("tet_p1")))
+    _same(A, oracle(p0))
+    assert abs(A.sum() - np.abs(np.linalg.det(
+        (p0[:, m.t[1:]] - p0[:, m.t[:1]]).transpose(2, 0, 1))).sum() / 6.0) < 1e-12
+    p1 = p0 * np.array([[1.5], [0.6], [1.1]])
+    b.update_points(p1)
+    A1 = mass.assemble(b)
+    assert plan_of(b) is fp and not fp.flag.item()
+    _same(A1, oracle(p1))
+
+
 def test_fused2_baseline_config2_full_size(options):
     """BASELINE configs[1] at full size through the v2 path: closed-form nnz, symmetry, zero
     row sums, exact energy of a linear field, agreement of the cold and warm paths, and a
