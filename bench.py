@@ -323,7 +323,8 @@ def run_gpu(args):
         da = DistributedAssembler(laplace, basis, l2g, Nglob, ranges, reuse_buffers=True,
                                   graph_exchange=os.environ.get("SKB_GRAPH_EXCHANGE") == "1",
                                   pipeline=os.environ.get("SKB_PIPELINE", "1") == "1",
-                                  sm_reserve=int(os.environ.get("SKB_SM_RESERVE", "0")))
+                                  sm_reserve=int(os.environ.get("SKB_SM_RESERVE", "0")),
+                                  depth=int(os.environ.get("SKB_PIPE_DEPTH", "2")))
         A = da.assemble()
     torch.cuda.synchronize()
     cold_ms = 1e3 * (time.perf_counter() - t0)

@@ -277,19 +277,22 @@ class DistributedAssembler:
     """
 
     def __init__(self, form, basis, l2g, N, ranges=None, group=None, reuse_buffers=False,
-                 graph_exchange=False, pipeline=False, sm_reserve=0):
+                 graph_exchange=False, pipeline=False, sm_reserve=0, depth=2):
         # graph_exchange=True also captures the NCCL all-to-all in the CUDA graph; it hung
         # on the B200 box with torch 2.11 / NCCL 2.28 (round 1), so it is opt-in.
         import torch.distributed as dist
         self.form, self.basis, self.N, self.group = form, basis, int(N), group
         self.reuse_buffers = bool(reuse_buffers)
         self.graph_exchange = bool(graph_exchange)
-        # pipeline=True (with reuse_buffers): two output buffer sets; the interface
+        # pipeline=True (with reuse_buffers): `depth` output buffer sets; the interface
         # exchange + ordered add of step i run on a side stream while the local
         # kernels of step i+1 run on the caller's stream.  The returned block
         # carries the event that completes it (DistributedCSR.wait) and is
-        # overwritten two calls later.
+        # overwritten `depth` calls later (a third set was measured at 2 GPUs: same
+        # 0.194 ms per step, so the wait for a set's own exchange is not what the step
+        # loses against one GPU - profiles/r2_trace_2gpu.md).
         self.pipeline = bool(pipeline) and self.reuse_buffers
+        self.depth = max(2, int(depth))
         # sm_reserve (pipelined mode): SMs the persistent fused kernel leaves free so
         # that the NCCL kernel of the previous step's exchange can run beside it
         self.sm_reserve = int(sm_reserve)
@@ -363,7 +366,7 @@ class DistributedAssembler:
             dev = ex.slot_map.device
             self._comm = torch.cuda.Stream(device=dev)
             self._sets, self._flip = [], 0
-            for _ in range(2):
+            for _ in range(self.depth):
                 out = torch.empty(ex.nnz + ex.nsend, dtype=torch.float64, device=dev)
                 self.form.assemble_device(self.basis, out=out, slot_map=ex.slot_map)  # plan, warm
                 ex.finish(out)                                                         # NCCL warm
@@ -380,7 +383,7 @@ class DistributedAssembler:
                 self._sets.append({"out": out, "graph": g,
                                    "computed": torch.cuda.Event(), "done": torch.cuda.Event()})
         st = self._sets[self._flip]
-        self._flip ^= 1
+        self._flip = (self._flip + 1) % self.depth
         cur.wait_event(st["done"])            # the exchange that last read this set is over
         st["graph"].replay()
         st["computed"].record(cur)
