@@ -747,6 +747,11 @@ def asm(form, *args, to=None, **kwargs):
                   for ix, combo in zip(product(*(range(len(x)) for x in lists)), product(*lists))]
         out = sum(blocks)
         return out.todefault() if to is None else to(blocks)
+    # the reference hands the position of the basis in its (one-element) lists to the form
+    # as w.idx (assembly/__init__.py:91-93); library forms with a dedicated kernel never
+    # read w, for them the kwarg would only disable the kernel
+    if getattr(form, "native", None) is None and "idx" not in kwargs:
+        kwargs["idx"] = (0,) * len(args)
     if to is not None:
         return to([form.coo_data(*args, **kwargs)])
     return form.assemble(*args, **kwargs)

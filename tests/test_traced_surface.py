@@ -114,5 +114,15 @@ def test_gpu_traced_surface():
     A = fem.asm(scaled_mass, b1, alpha=3.0)
     assert np.array_equal(A.indices, g["asm_indices"])
     np.testing.assert_allclose(A.data, g["asm_data"], rtol=1e-12)
+    # asm hands the basis position to the form as w.idx, also for a single basis
+    # (assembly/__init__.py:91-93)
+    seen = []
+
+    def idx_mass(u, v, w):
+        seen.append(w['idx'])
+        return 3.0 * u * v
+    A2 = fem.asm(idx_mass, b1)
+    assert seen and all(ix == (0,) for ix in seen)
+    np.testing.assert_allclose(A2.data, g["asm_data"], rtol=1e-12)
     with pytest.raises(ValueError, match="wrong size"):
         b1.interpolate(prev[:-1])
