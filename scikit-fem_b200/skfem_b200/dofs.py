@@ -127,48 +127,68 @@ class DofsView:
     __add__ = __or__
 
 
+class _LazyBlock:
+    """Descriptor: a ``_block`` table built on first access (a million-entry arange per
+    Basis is a millisecond of the cold path that most assemblies never look at)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __get__(self, obj, owner=None):
+        if obj is None:
+            return self
+        tab = obj.__dict__.get(self.name)
+        if tab is None:
+            nd, n, off = obj._blocks[self.name]
+            tab = _block(nd, n, off) if n else np.empty((0, 0), dtype=np.int32)
+            obj.__dict__[self.name] = tab
+        return tab
+
+
 class Dofs:
+    nodal_dofs = _LazyBlock("nodal_dofs")
+    edge_dofs = _LazyBlock("edge_dofs")
+    facet_dofs = _LazyBlock("facet_dofs")
+    interior_dofs = _LazyBlock("interior_dofs")
 
     def __init__(self, topo, element, offset=0):
         self.topo = topo
         self.element = element
         nel = topo.nelements
         three_d = element.dim == 3
-
-        self.nodal_dofs = _block(element.nodal_dofs, topo.nvertices, offset)
-        offset += self.nodal_dofs.size
-
-        if three_d and element.edge_dofs > 0:
-            self.edge_dofs = _block(element.edge_dofs, topo.nedges, offset)
-            offset += self.edge_dofs.size
-        else:
-            self.edge_dofs = np.empty((0, 0), dtype=np.int32)
-
-        if element.facet_dofs > 0:
-            self.facet_dofs = _block(element.facet_dofs, topo.nfacets, offset)
-            offset += self.facet_dofs.size
-        else:
-            self.facet_dofs = np.empty((0, 0), dtype=np.int32)
-
-        self.interior_dofs = _block(element.interior_dofs, nel, offset)
+        # (dofs per entity, entities, first index) of the four blocks; the tables themselves
+        # are built lazily, entity-major like the reference (dofs.py:264-334)
+        self._blocks = {}
+        off0 = offset
+        self._blocks["nodal_dofs"] = (element.nodal_dofs, topo.nvertices, offset)
+        offset += element.nodal_dofs * topo.nvertices
+        nedge = element.edge_dofs if three_d else 0
+        self._blocks["edge_dofs"] = (nedge, topo.nedges if nedge else 0, offset)
+        offset += nedge * (topo.nedges if nedge else 0)
+        nfac = element.facet_dofs
+        self._blocks["facet_dofs"] = (nfac, topo.nfacets if nfac else 0, offset)
+        offset += nfac * (topo.nfacets if nfac else 0)
+        self._blocks["interior_dofs"] = (element.interior_dofs, nel, offset)
+        if element.interior_dofs == 0:      # the reference's (0, nel) table
+            self.__dict__["interior_dofs"] = np.empty((0, nel), dtype=np.int32)
 
         # nodal rows: nodal_dofs[c, v] == nd*v + c + offset0, so the gather
         # nodal_dofs[:, t[k]] is plain integer arithmetic on t (and for one
         # DOF per vertex element_dofs IS t: no copy, no extra upload)
-        nd, off0 = element.nodal_dofs, np.int32(self.nodal_dofs[0, 0]) if self.nodal_dofs.size else 0
+        nd = element.nodal_dofs
         self.nodal_is_t = False
         if nd == 1 and off0 == 0:
             parts = [topo.t]
             self.nodal_is_t = True
         else:
             parts = [np.int32(nd) * topo.t[k][None, :]
-                     + (np.arange(nd, dtype=np.int32) + off0)[:, None]
+                     + (np.arange(nd, dtype=np.int32) + np.int32(off0))[:, None]
                      for k in range(topo.t.shape[0])] if nd > 0 else []
-        if self.edge_dofs.size:
+        if nedge:
             parts += [self.edge_dofs[:, topo.t2e[k]] for k in range(topo.t2e.shape[0])]
-        if element.dim >= 2 and self.facet_dofs.size:
+        if element.dim >= 2 and nfac:
             parts += [self.facet_dofs[:, topo.t2f[k]] for k in range(topo.t2f.shape[0])]
-        if self.interior_dofs.size:
+        if element.interior_dofs:
             parts.append(self.interior_dofs)
         if len(parts) == 1 and self.nodal_is_t:
             self.element_dofs = topo.t
@@ -176,7 +196,7 @@ class Dofs:
             self.nodal_is_t = False
             self.element_dofs = np.ascontiguousarray(np.vstack(parts), dtype=np.int32)
         # == max(element_dofs) + 1: every vertex/edge/facet/cell is referenced
-        self.N = int(offset + self.interior_dofs.size)
+        self.N = int(offset + element.interior_dofs * nel)
 
     def on_facets(self, facets):
         """All DOFs attached to the vertices / edges / facets of the given facets,
