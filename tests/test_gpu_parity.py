@@ -150,8 +150,19 @@ def test_determinism_and_plan_reuse():
     assert np.array_equal(A1.data, A3.data)      # cold == cold, bitwise
     assert np.array_equal(A2.data, A2b.data) and np.array_equal(A2.data, A4.data)  # warm == warm
     np.testing.assert_allclose(A2.data, A1.data, rtol=RTOL, atol=RTOL * np.abs(A1.data).max())
-    M1, M2 = mass.assemble(b), mass.assemble(b)  # generic warm path reuses the plan
-    assert np.array_equal(M1.data, M2.data)
+    # mass on P1 tets has a fused warm path too (round 2): cold vs warm within tolerance,
+    # warm vs warm bitwise; with the fused path off the generic warm path reuses the plan
+    M1, M2, M3 = mass.assemble(b), mass.assemble(b), mass.assemble(b)
+    assert np.array_equal(M2.data, M3.data)
+    np.testing.assert_allclose(M2.data, M1.data, rtol=RTOL, atol=RTOL * np.abs(M1.data).max())
+    from skfem_b200 import form as F
+    F.set_options(fused=False)
+    try:
+        b3 = fem.Basis(m, fem.ElementTetP1())
+        G1, G2 = mass.assemble(b3), mass.assemble(b3)
+        assert np.array_equal(G1.data, G2.data) and np.array_equal(G1.data, M1.data)
+    finally:
+        F.set_options(fused=True)
 
 
 def test_element_subset_and_edge_cases():
