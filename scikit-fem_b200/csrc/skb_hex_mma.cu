@@ -9,10 +9,10 @@
 // i.e. a 27 x K by K x 27 product per element: the one part of this library
 // whose work really is a dense contraction (FP64 DMMA for C4).  It
 // runs on mma.sync.m8n8k4.f64 (tcgen05 has no FP64 kind).  Hex2 parity is
-// value-level (rtol 1e-11; its tables already differ from the reference's
-// generated Horner forms by a few ulp), so the quadrature sum may be reordered
-// and the symmetric sqrt(dx) scaling used; ElementHex1 (bit-exact parity) keeps
-// the scalar kernel in skb_local.cu.
+// value-level (CSR values within rtol 1e-12 of the reference; the tables are the
+// reference's own), so the quadrature sum may be reordered and the symmetric
+// sqrt(dx) scaling used; ElementHex1 (bit-exact local data) keeps the scalar
+// kernel in skb_local.cu.
 //
 // One WARP per element, 8 elements per CTA, one CTA per SM.  Quadrature points are
 // processed in chunks of 32 (lane = point).  The chunk's reference tables (dphi of
