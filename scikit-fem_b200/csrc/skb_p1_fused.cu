@@ -98,17 +98,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+  // C loop around try_wait: no PTX labels, so the function can be inlined any number of times
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
 }
 // TMA bulk copy global -> shared, completion counted on an mbarrier; marked evict-first in L2:
 // the records are read once per step and must not push the vertex coordinates / tile partials
@@ -514,11 +516,12 @@ extern "C" int skb_l2_window(const void *ptr, int64_t bytes, void *stream) {
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
     if (max_persist <= 0 || max_window <= 0) return SKB_OK;   // feature absent: nothing to do
-    static int64_t limit_set = 0;
+    static int64_t limit_set[64] = {0};                 // per device (the limit is per device)
     const int64_t want = bytes < max_persist ? bytes : max_persist;
-    if (want > limit_set) {
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (want > limit_set[slot] || dev >= 64) {
       SKB_CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want));
-      limit_set = want;
+      limit_set[slot] = want;
     }
     v.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
     v.accessPolicyWindow.num_bytes = (size_t)(bytes < max_window ? bytes : max_window);
