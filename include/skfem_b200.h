@@ -144,6 +144,18 @@ int skb_plan_rows_sort(const int32_t *dofs_v, const int32_t *dofs_u, int32_t nbv
 int skb_plan_rows_emit(int64_t nrows, int64_t nnz, int64_t nkeep, const uint32_t *candstart,
                        const int32_t *indptr, const uint32_t *ucol, const uint32_t *uoff,
                        int32_t *indices, uint32_t *segptr, void *stream);
+/* Mesh.build_entities (mesh/mesh.py:1065-1082: np.sort + np.unique(axis=1) over the vertex
+ * tuples of all local edges / facets) through the same row-bucket machinery: the sorted unique
+ * edges are the CSR pattern whose incidences are (local vertex i, element e) with the
+ * surviving columns {j adjacent to i : vertex j > vertex i}; triangular facets use row = id of
+ * the edge of the two smallest vertices, col = the largest vertex.  skb_entity_masks forms the
+ * masks (bit j of mask[i*nel+e] <=> j in adj_host[i] and tu[j][e] > vmax[i][e]); pass them to
+ * skb_plan_rows_count with local == NULL and drop_zeros == 2.  skb_plan_slot_of_entry inverts
+ * perm / segptr (slot[k] = CSR slot of surviving COO entry k), which gives t2e / t2f.       */
+int skb_entity_masks(const int32_t *tu, int32_t nbu, int32_t nbv, int64_t nel,
+                     const int32_t *vmax, const uint32_t *adj_host, uint32_t *mask, void *stream);
+int skb_plan_slot_of_entry(const uint32_t *segptr, const uint32_t *perm, int64_t nnz,
+                           int32_t *slot, void *stream);
 
 /* ---- numeric phase: replaces csr_sum_duplicates (coo_data.py:36) ----
  * data[s] = sum of local[perm[k]], k in [segptr[s], segptr[s+1]), added

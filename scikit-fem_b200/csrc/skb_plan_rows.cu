@@ -143,7 +143,9 @@ __global__ void rows_count_kernel(const int32_t *__restrict__ dofs_v, int nbv, i
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < ninc;
        idx += (int64_t)gridDim.x * blockDim.x) {
     uint32_t m = full;
-    if (drop_zeros && local) {
+    if (drop_zeros == 2) {
+      m = mask[idx] & full;                              // masks supplied by the caller
+    } else if (drop_zeros && local) {
       const int64_t i = idx / nel, e = idx - i * nel;
       m = 0;
       for (int j = 0; j < nbu; ++j)                      // coo_data.py:35
@@ -467,6 +469,42 @@ __global__ void rows_emit_kernel(int64_t nrows, const uint32_t *__restrict__ can
   if (blockIdx.x == 0 && threadIdx.x == 0) segptr[nnz] = (uint32_t)nkeep;
 }
 
+// ---- mesh entities through the same machinery ----------------------------------------------
+// Mesh.build_entities (mesh/mesh.py:1065-1082: np.sort + np.unique(axis=1) of the vertex tuples
+// of all local edges / facets) is the same problem as the plan: the unique sorted pairs
+// (row = smallest vertex, col = other vertex) of an edge list are the CSR pattern of the
+// "matrix" whose incidences are (local vertex i, element e) and whose surviving columns are
+// the local vertices j adjacent to i with a larger global index.  Triangular facets: row = id
+// of the edge of the two smallest vertices, col = largest vertex.  This kernel forms those
+// masks: bit j of mask[i * nel + e] <=> j in adj[i] and tu[j][e] > vmax[i][e].
+struct EntityAdj { uint32_t adj[32]; };
+__global__ void entity_mask_kernel(const int32_t *__restrict__ tu, int nbu, int nbv, int64_t nel,
+                                   const int32_t *__restrict__ vmax, EntityAdj a,
+                                   uint32_t *__restrict__ mask) {
+  const int64_t n = (int64_t)nbv * nel;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / nel, e = idx - i * nel;
+    const int32_t vm = vmax[idx];
+    uint32_t m = 0, cand = a.adj[i];
+    while (cand) {
+      const int j = __ffs(cand) - 1;
+      cand &= cand - 1;
+      if (j < nbu && tu[(int64_t)j * nel + e] > vm) m |= 1u << j;
+    }
+    mask[idx] = m;
+  }
+}
+
+// slot[k] = CSR slot of COO entry k for every surviving entry (others keep their value)
+__global__ void slot_of_entry_kernel(const uint32_t *__restrict__ segptr,
+                                     const uint32_t *__restrict__ perm, int64_t nnz,
+                                     int32_t *__restrict__ slot) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nnz;
+       s += (int64_t)gridDim.x * blockDim.x)
+    for (uint32_t x = segptr[s]; x < segptr[s + 1]; ++x) slot[perm[x]] = (int32_t)s;
+}
+
 static inline int rows_blocks(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -595,6 +633,38 @@ extern "C" int skb_plan_rows_emit(int64_t nrows, int64_t nnz, int64_t nkeep,
   if (g < 1) g = 1;
   rows_emit_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(nrows, candstart, indptr, ucol,
                                                                   uoff, indices, segptr, nnz, nkeep);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// Masks for mesh entities (see entity_mask_kernel): tu int32[nbu][nel] vertex ids, vmax
+// int32[nbv][nel], adj_host uint32[nbv] (nbv, nbu <= 32); mask uint32[nbv * nel] out.  Feed it
+// to skb_plan_rows_count with drop_zeros == 2 and local == NULL.
+extern "C" int skb_entity_masks(const int32_t *tu, int32_t nbu, int32_t nbv, int64_t nel,
+                                const int32_t *vmax, const uint32_t *adj_host, uint32_t *mask,
+                                void *stream) {
+  using namespace skb;
+  if (!tu || !vmax || !adj_host || !mask || nbu <= 0 || nbu > 32 || nbv <= 0 || nbv > 32 ||
+      nel < 0)
+    return SKB_EINVAL;
+  if (nel == 0) return SKB_OK;
+  EntityAdj a;
+  for (int i = 0; i < 32; ++i) a.adj[i] = i < nbv ? adj_host[i] : 0u;
+  entity_mask_kernel<<<rows_blocks((int64_t)nbv * nel, 256), 256, 0, (cudaStream_t)stream>>>(
+      tu, nbu, nbv, nel, vmax, a, mask);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// slot[perm[x]] = s for x in [segptr[s], segptr[s+1]): the CSR slot of every surviving COO entry
+// (slot int32[ncoo], entries that did not survive are left untouched).
+extern "C" int skb_plan_slot_of_entry(const uint32_t *segptr, const uint32_t *perm, int64_t nnz,
+                                      int32_t *slot, void *stream) {
+  using namespace skb;
+  if (nnz < 0 || !segptr || !slot) return SKB_EINVAL;
+  if (nnz == 0) return SKB_OK;
+  slot_of_entry_kernel<<<rows_blocks(nnz, 256), 256, 0, (cudaStream_t)stream>>>(segptr, perm, nnz,
+                                                                                slot);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -201,7 +201,7 @@ def _mask_plan_put(ubasis, vbasis, nz, plan):
     del lst[:-MASK_PLANS_KEPT]
 
 
-def _build_plan_rows(plan, dofs_v, dofs_u, nel, nrows, local, drop_zeros):
+def _build_plan_rows(plan, dofs_v, dofs_u, nel, nrows, local, drop_zeros, mask=None):
     """Row buckets + per-row sorts (csrc/skb_plan_rows.cu).  Returns False when a limit of
     that path is hit (the caller then takes the radix-sort path)."""
     torch = _torch()
@@ -213,14 +213,18 @@ def _build_plan_rows(plan, dofs_v, dofs_u, nel, nrows, local, drop_zeros):
 
     def u32(n):
         return torch.empty(max(int(n), 1), dtype=i32, device=dev)
-    mask = u32(nbv * nel)
+    # mask (optional, int32 tensor of nbv * nel words): the surviving columns of every
+    # incidence, supplied by the caller instead of being derived from `local`
+    drop = 2 if mask is not None else (1 if drop_zeros else 0)
+    if mask is None:
+        mask = u32(nbv * nel)
     rc = torch.empty(nrows, dtype=i64, device=dev)
     sums = u32(4096)
     incstart, candstart = u32(nrows + 1), u32(nrows + 1)
     counts = (C.c_int64 * 2)()
     code = lib.skb_plan_rows_count(
         dofs_v.data_ptr(), nbv, nbu, nel, nrows, None if local is None else local.data_ptr(),
-        1 if drop_zeros else 0, mask.data_ptr(), rc.data_ptr(), sums.data_ptr(),
+        drop, mask.data_ptr(), rc.data_ptr(), sums.data_ptr(),
         incstart.data_ptr(), candstart.data_ptr(), counts, _stream())
     if code == _lib.SKB_ETOOBIG:
         return False
@@ -253,7 +257,7 @@ def _build_plan_rows(plan, dofs_v, dofs_u, nel, nrows, local, drop_zeros):
     return True
 
 
-def build_plan(dofs_v, dofs_u, nel, shape, local, drop_zeros=True, method=None):
+def build_plan(dofs_v, dofs_u, nel, shape, local, drop_zeros=True, method=None, mask=None):
     """The CSR structure + the per-slot lists of COO entries, built on the device:
     ``method`` "rows" (default, ``set_options(plan_method=...)``): row buckets and per-row
     sorts (skb_plan_rows_*); "sort": one global radix sort (skb_plan_symbolic +
@@ -277,9 +281,11 @@ def build_plan(dofs_v, dofs_u, nel, shape, local, drop_zeros=True, method=None):
         plan.segptr = torch.zeros(1, dtype=i32, device=dev)
         plan.perm = torch.zeros(0, dtype=i32, device=dev)
         return plan
-    if (method or _CONFIG["plan_method"]) == "rows" and \
-            _build_plan_rows(plan, dofs_v, dofs_u, nel, nrows, local, drop_zeros):
-        return plan
+    if mask is not None or (method or _CONFIG["plan_method"]) == "rows":
+        if _build_plan_rows(plan, dofs_v, dofs_u, nel, nrows, local, drop_zeros, mask):
+            return plan
+        if mask is not None:
+            return None                                  # (mesh entities: the caller falls back)
     keys_a = torch.empty(ncoo, dtype=i64, device=dev)
     keys_b = torch.empty(ncoo, dtype=i64, device=dev)
     vals_a = torch.empty(ncoo, dtype=i32, device=dev)

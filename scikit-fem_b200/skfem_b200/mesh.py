@@ -26,16 +26,128 @@ def _cuda_ready():
         return False
 
 
+def _pair_plan(tv, tu, adj, vmax, nrows):
+    """Sorted unique (row, col) pairs - rows from ``tv`` (nbv, nel), cols from ``tu`` (nbu,
+    nel), kept where ``tu[j] > vmax[i]`` for j in ``adj[i]`` - by the row-bucket plan builder
+    (csrc/skb_plan_rows.cu, skb_entity_masks): (row_of_slot, col_of_slot, slot_of_entry) or
+    None when a limit of that path is hit."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    from .form import build_plan
+    lib = _lib.lib()
+    nbv, nel = int(tv.shape[0]), int(tv.shape[1])
+    nbu = int(tu.shape[0])
+    dev = tv.device
+    mask = torch.empty(nbv * nel, dtype=torch.int32, device=dev)
+    adj_c = (C.c_uint32 * nbv)(*[int(a) for a in adj])
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.skb_entity_masks(tu.data_ptr(), nbu, nbv, nel, vmax.data_ptr(), adj_c,
+                                    mask.data_ptr(), stream), "skb_entity_masks")
+    plan = build_plan(tv, tu, nel, (nrows, nrows), None, mask=mask)
+    if plan is None:
+        return None
+    slot = torch.full((nbu * nbv * nel,), -1, dtype=torch.int32, device=dev)
+    _lib.check(lib.skb_plan_slot_of_entry(plan.segptr.data_ptr(), plan.perm.data_ptr(), plan.nnz,
+                                          slot.data_ptr(), stream), "skb_plan_slot_of_entry")
+    counts = (plan.indptr[1:] - plan.indptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(nrows, device=dev, dtype=torch.int64), counts)
+    return rows, plan.indices.long(), slot
+
+
+def _edges_rows(tt, indices, nv):
+    """Edges (k = 2) of a mesh by the library's own kernels: entities (2, nedges) sorted
+    lexicographically and the incidence (len(indices), nel), both device int64 tensors."""
+    import torch
+    nn, nel = int(tt.shape[0]), int(tt.shape[1])
+    adj = [0] * nn
+    for a, b in indices:
+        adj[a] |= 1 << b
+        adj[b] |= 1 << a
+    res = _pair_plan(tt, tt, adj, tt, nv)
+    if res is None:
+        return None
+    rows, cols, slot = res
+    e = torch.arange(nel, device=tt.device, dtype=torch.int64)
+    inc = []
+    for a, b in indices:      # entry (j * nn + i) * nel + e with i = the smaller vertex
+        k = torch.where(tt[a] < tt[b], b * nn + a, a * nn + b).long() * nel + e
+        inc.append(slot[k].long())
+    return torch.stack([rows, cols]), torch.stack(inc)
+
+
 def _build_entities_device(t, indices, nv, sort):
-    """``Mesh.build_entities`` with the sort / unique on the GPU (SURVEY 8f rank
-    4: entity keys as packed 64-bit integers); same results as the host path,
-    returned as host arrays because the numbering API is host numpy."""
+    """``Mesh.build_entities`` on the GPU; same results as the host path,
+    returned as host arrays because the numbering API is host numpy.  Edges of any mesh and the
+    triangular facets of tetrahedra go through the library's own row-bucket sort (the unique
+    sorted pairs are a CSR pattern, csrc/skb_plan_rows.cu); quadrilateral facets and
+    ``sort=False`` numberings use torch's sort / unique on packed integer keys."""
     import torch
     dev = torch.device("cuda", torch.cuda.current_device())
     k, n = len(indices[0]), t.shape[1]
-    tt = torch.from_numpy(np.ascontiguousarray(t)).to(dev).long()
+    tdt = t.dtype
+    tt32 = torch.from_numpy(np.ascontiguousarray(t, dtype=np.int32)).to(dev)
+
+    def host(ent, inc):
+        return (np.ascontiguousarray(ent.to(torch.int32).cpu().numpy().astype(tdt, copy=False)),
+                inc.to(torch.int32).cpu().numpy().astype(np.int64))
+    if sort and k == 2:
+        res = _edges_rows(tt32, [tuple(ix) for ix in indices], nv)
+        if res is not None:
+            return host(*res)
+    if sort and k == 3 and t.shape[0] == 4:
+        # facet (a < b < c) = (edge of the two smallest vertices, largest vertex)
+        ledges = [(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]
+        er = _edges_rows(tt32, ledges, nv)
+        if er is not None:
+            edges, t2e = er
+            nedges = int(edges.shape[1])
+            adj = [sum(1 << j for j in range(4) if j not in le) for le in ledges]
+            vmax = torch.stack([torch.maximum(tt32[a], tt32[b]) for a, b in ledges]).contiguous()
+            res = _pair_plan(t2e.to(torch.int32).contiguous(), tt32, adj, vmax, nedges)
+            if res is not None:
+                rows, cols, slot = res
+                ent = torch.stack([edges[0][rows], edges[1][rows], cols])
+                eidx = {le: i for i, le in enumerate(ledges)}
+                e = torch.arange(n, device=dev, dtype=torch.int64)
+                inc = []
+                for ix in indices:
+                    ix = tuple(int(v) for v in ix)
+                    vals = torch.stack([tt32[v] for v in ix])            # (3, nel)
+                    order = torch.argsort(vals, dim=0)                    # local positions
+                    loc = torch.tensor(ix, device=dev)[order]             # (3, nel) local ids
+                    lo, mid, hi = loc[0], loc[1], loc[2]
+                    le = torch.zeros(n, dtype=torch.int64, device=dev)
+                    for (a, b), i in eidx.items():
+                        le = torch.where(((lo == a) & (mid == b)) | ((lo == b) & (mid == a)),
+                                         torch.full_like(le, i), le)
+                    inc.append(slot[(hi * 6 + le) * n + e].long())
+                return host(ent, torch.stack(inc))
+    tt = tt32.long()
     stacked = torch.cat([tt[list(ix)] for ix in indices], dim=1)          # (k, n * len(indices))
     canon = torch.sort(stacked, dim=0).values
+    if k == 4 and float(nv) ** 4 >= 2.0 ** 62:
+        # two levels: dense rank of the leading pair, then (rank, trailing pair) - both fit
+        hi_key = canon[0] * nv + canon[1]
+        uhi, rhi = torch.unique(hi_key, sorted=True, return_inverse=True)
+        key = (rhi * nv + canon[2]) * nv + canon[3]
+        ukey, inverse = torch.unique(key, sorted=True, return_inverse=True)
+        incidence = inverse.reshape(len(indices), n).cpu().numpy()
+        if not sort:
+            first = torch.full((ukey.shape[0],), inverse.shape[0], dtype=torch.int64, device=dev)
+            first.scatter_reduce_(0, inverse, torch.arange(inverse.shape[0], device=dev), "amin")
+            return (np.ascontiguousarray(stacked[:, first].to(torch.int32).cpu().numpy()
+                                         .astype(tdt, copy=False)), incidence)
+        ent = torch.empty((4, ukey.shape[0]), dtype=torch.int64, device=dev)
+        ent[3] = ukey % nv
+        rest = ukey // nv
+        ent[2] = rest % nv
+        lead = uhi[rest // nv]
+        ent[1] = lead % nv
+        ent[0] = lead // nv
+        return ent.to(torch.int32).cpu().numpy().astype(tdt, copy=False), incidence
+    if float(nv) ** k >= 2.0 ** 62:
+        return None                                   # keys do not pack: host path
     key = canon[0]
     for r in range(1, k):
         key = key * nv + canon[r]
@@ -47,12 +159,12 @@ def _build_entities_device(t, indices, nv, sort):
         first = torch.full((ukey.shape[0],), inverse.shape[0], dtype=torch.int64, device=dev)
         first.scatter_reduce_(0, inverse, torch.arange(inverse.shape[0], device=dev), "amin")
         return (np.ascontiguousarray(stacked[:, first].to(torch.int32).cpu().numpy()
-                                     .astype(t.dtype, copy=False)), incidence)
+                                     .astype(tdt, copy=False)), incidence)
     ent = torch.empty((k, ukey.shape[0]), dtype=torch.int64, device=dev)
     for r in range(k - 1, -1, -1):
         ent[r] = ukey % nv
         ukey = ukey // nv
-    return ent.to(torch.int32).cpu().numpy().astype(t.dtype, copy=False), incidence
+    return ent.to(torch.int32).cpu().numpy().astype(tdt, copy=False), incidence
 
 
 class Mesh:
@@ -134,13 +246,15 @@ class Mesh:
         entity incidence."""
         k = len(indices[0])
         nv = int(t.max()) + 1 if t.size else 1
+        if t.shape[1] >= (1 << 16) and _cuda_ready():
+            res = _build_entities_device(t, indices, nv, sort)
+            if res is not None:
+                return res
         if nv ** k < (1 << 62):
             # a sorted vertex tuple packs into one int64 whose order is the
             # lexicographic order of the tuple: 1-D unique instead of numpy's
             # structured-dtype argsort (2.5x faster on the host); with a CUDA
-            # device and a large mesh the same sort/unique runs there (100x)
-            if t.shape[1] >= (1 << 16) and _cuda_ready():
-                return _build_entities_device(t, indices, nv, sort)
+            # device and a large mesh the numbering runs there (above)
             stacked = np.hstack([t[ix] for ix in indices])
             canon = np.sort(stacked, axis=0).astype(np.int64)
             key = canon[0]
