@@ -152,6 +152,14 @@ int skb_plan_rows_emit(int64_t nrows, int64_t nnz, int64_t nkeep, const uint32_t
  * masks (bit j of mask[i*nel+e] <=> j in adj_host[i] and tu[j][e] > vmax[i][e]); pass them to
  * skb_plan_rows_count with local == NULL and drop_zeros == 2.  skb_plan_slot_of_entry inverts
  * perm / segptr (slot[k] = CSR slot of surviving COO entry k), which gives t2e / t2f.       */
+/* MeshTet.init_tensor / MeshHex.init_tensor (mesh/mesh_tet_1.py:326-393,
+ * mesh/mesh_hex_1.py:97-155) on the device (csrc/skb_mesh.cu): x, y, z sorted device
+ * coordinates; corner_host[ntypes][nnodes] the cell corners (0..7) of every element type (six
+ * Kuhn tetrahedra, or the hexahedron); p double[3][npx*npy*npz], t int32[nnodes][ntypes*ncells],
+ * element order type-major.  Bit for bit the host generator's arrays.                      */
+int skb_mesh_tensor(const double *x, const double *y, const double *z, int32_t npx, int32_t npy,
+                    int32_t npz, int32_t ntypes, int32_t nnodes, const int32_t *corner_host,
+                    double *p, int32_t *t, void *stream);
 int skb_entity_masks(const int32_t *tu, int32_t nbu, int32_t nbv, int64_t nel,
                      const int32_t *vmax, const uint32_t *adj_host, uint32_t *mask, void *stream);
 int skb_plan_slot_of_entry(const uint32_t *segptr, const uint32_t *perm, int64_t nnz,

@@ -525,6 +525,42 @@ class Mesh:
         return self._dev[key]
 
 
+def _tensor_mesh_device(cls, x, y, z, corners):
+    """``init_tensor`` on the GPU for large grids (csrc/skb_mesh.cu): the same p / t as the host
+    generator, the host copies fetched into pinned memory and the device copies kept as the
+    mesh's device arrays (no upload later).  None if no GPU / small grid / int32 overflow."""
+    npx, npy, npz = len(x), len(y), len(z)
+    ncells = (npx - 1) * (npy - 1) * (npz - 1)
+    if ncells * len(corners) < (1 << 16) or not _cuda_ready():
+        return None
+    import ctypes as C
+    import torch
+    from . import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    xs, ys, zs = (torch.from_numpy(np.sort(np.asarray(v, dtype=np.float64))).to(dev)
+                  for v in (x, y, z))
+    nn, npts = len(corners[0]), npx * npy * npz
+    p = torch.empty((3, npts), dtype=torch.float64, device=dev)
+    t = torch.empty((nn, ncells * len(corners)), dtype=torch.int32, device=dev)
+    tab = (C.c_int32 * (len(corners) * nn))(*[int(v) for row in corners for v in row])
+    code = _lib.lib().skb_mesh_tensor(xs.data_ptr(), ys.data_ptr(), zs.data_ptr(), npx, npy, npz,
+                                      len(corners), nn, tab, p.data_ptr(), t.data_ptr(),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if code == _lib.SKB_ETOOBIG:
+        return None
+    _lib.check(code, "skb_mesh_tensor")
+    ph = torch.empty(p.shape, dtype=p.dtype, pin_memory=True)
+    th = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    ph.copy_(p, non_blocking=True)
+    th.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    m = cls(ph.numpy(), th.numpy())
+    m._pinned = (ph, th)                       # keeps the pinned buffers alive
+    m._dev[str(dev)] = (p, t)
+    m._nvertices = npts
+    return m
+
+
 def _tensor_grid(x, y, z):
     """Vertices of a tensor grid (vertex index = iy + npy*ix + npy*npx*iz) and
     the eight corner rows of each cell, cells enumerated the same way."""
@@ -594,9 +630,12 @@ class MeshTet(Mesh):
         """Tensor-product grid, each cell split into the six Kuhn tetrahedra
         that share the body diagonal (corner 0 -> corner 7); the element order
         is type-major: all cells' first tet, then all second tets, ..."""
-        p, c, _ = _tensor_grid(x, y, z)
         kuhn = ([0, 1, 5, 7], [0, 1, 4, 7], [0, 2, 4, 7],
                 [0, 3, 5, 7], [0, 2, 6, 7], [0, 3, 6, 7])
+        m = _tensor_mesh_device(cls, x, y, z, kuhn)
+        if m is not None:
+            return m
+        p, c, _ = _tensor_grid(x, y, z)
         return cls(p, np.hstack([c[rows] for rows in kuhn]))
 
     @classmethod
@@ -663,6 +702,9 @@ class MeshHex(Mesh):
 
     @classmethod
     def init_tensor(cls, x, y, z):
+        m = _tensor_mesh_device(cls, x, y, z, (list(range(8)),))
+        if m is not None:
+            return m
         p, c, _ = _tensor_grid(x, y, z)
         return cls(p, c)
 

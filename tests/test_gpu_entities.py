@@ -57,3 +57,31 @@ def test_tri_and_hex_entities(monkeypatch):
     xh = np.linspace(0, 1, 42)
     mh = fem.MeshHex.init_tensor(xh, xh, xh)              # 68 921 hexes: quad facets, 12 edges
     _check(monkeypatch, mh)
+
+
+def test_init_tensor_on_the_device_equals_the_host_generator(monkeypatch):
+    """MeshTet / MeshHex.init_tensor of large grids run on the GPU (csrc/skb_mesh.cu): p and t
+    bit for bit the host generator's (unsorted, non-uniform inputs included), and the device
+    copies are adopted as the mesh's device arrays."""
+    import torch
+    rng = np.random.default_rng(7)
+    x, y, z = rng.random(31), rng.random(27), rng.random(29)
+    for cls in (fem.MeshTet, fem.MeshHex):
+        if cls is fem.MeshHex:
+            x, y, z = rng.random(45), rng.random(41), rng.random(43)
+        md = cls.init_tensor(x, y, z)
+        assert md._dev, "device path not taken"
+        monkeypatch.setattr(M, "_cuda_ready", lambda: False)
+        mh = cls.init_tensor(x, y, z)
+        monkeypatch.undo()
+        assert not mh._dev
+        assert md.p.dtype == mh.p.dtype and md.t.dtype == mh.t.dtype
+        assert np.array_equal(md.p, mh.p) and np.array_equal(md.t, mh.t)
+        pd, td = next(iter(md._dev.values()))
+        assert torch.equal(pd.cpu(), torch.from_numpy(mh.p))
+        assert torch.equal(td.cpu(), torch.from_numpy(mh.t))
+    # the generated mesh assembles like any other
+    from skfem_b200.models.poisson import laplace
+    g = np.linspace(0, 1, 24)
+    A = laplace.assemble(fem.Basis(fem.MeshTet.init_tensor(g, g, g), fem.ElementTetP1()))
+    assert A.nnz == 24 ** 3 + 6 * 23 * 24 ** 2
