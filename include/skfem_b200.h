@@ -160,6 +160,11 @@ int skb_plan_rows_emit(int64_t nrows, int64_t nnz, int64_t nkeep, const uint32_t
 int skb_mesh_tensor(const double *x, const double *y, const double *z, int32_t npx, int32_t npy,
                     int32_t npz, int32_t ntypes, int32_t nnodes, const int32_t *corner_host,
                     double *p, int32_t *t, void *stream);
+/* Dofs.__init__ (assembly/dofs.py:264-334), element_dofs on the device: row r of the result is
+ * add_r + mul_r * src_r[e]; rows_dev = nrows records {int64 src (device pointer to an int32 row
+ * of t / t2e / t2f, 0 = the element index), int32 mul, int32 add}; out int32[nrows][nel].   */
+int skb_element_dofs(const void *rows_dev, int32_t nrows, int64_t nel, int32_t *out,
+                     void *stream);
 int skb_entity_masks(const int32_t *tu, int32_t nbu, int32_t nbv, int64_t nel,
                      const int32_t *vmax, const uint32_t *adj_host, uint32_t *mask, void *stream);
 int skb_plan_slot_of_entry(const uint32_t *segptr, const uint32_t *perm, int64_t nnz,

@@ -45,7 +45,38 @@ __global__ void mesh_tensor_cells_kernel(int npx, int npy, int npz, int ntypes, 
   }
 }
 
+// element_dofs rows (assembly/dofs.py:264-334): every row is  add + mul * src[e]  with src a
+// row of t / t2e / t2f (entity-major blocks: dof c of entity n is offset + c + nd * n) or the
+// element index itself (interior DOFs, src == NULL).
+struct DofRow { const int32_t *src; int32_t mul, add; };
+__global__ void element_dofs_kernel(const DofRow *__restrict__ rows, int nrows, int64_t nel,
+                                    int32_t *__restrict__ out) {
+  const int64_t n = (int64_t)nrows * nel;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / nel, e = idx - r * nel;
+    const DofRow d = rows[r];
+    const int32_t v = d.src ? d.src[e] : (int32_t)e;
+    out[idx] = d.add + d.mul * v;
+  }
+}
+
 }  // namespace skb
+
+// rows_dev: nrows device records {int64 src pointer (0 = element index), int32 mul, int32 add};
+// out int32[nrows][nel].
+extern "C" int skb_element_dofs(const void *rows_dev, int32_t nrows, int64_t nel, int32_t *out,
+                                void *stream) {
+  using namespace skb;
+  if (!rows_dev || !out || nrows <= 0 || nel < 0) return SKB_EINVAL;
+  if (nel == 0) return SKB_OK;
+  int64_t g = ((int64_t)nrows * nel + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  element_dofs_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const DofRow *>(rows_dev), nrows, nel, out);
+  count_launch();
+  return (int)cudaGetLastError();
+}
 
 // x, y, z: sorted coordinates on the device (npx, npy, npz doubles); corner_host: ntypes x
 // nnodes corner indices (0..7); p: double[3][npx*npy*npz], t: int32[nnodes][ntypes*ncells].

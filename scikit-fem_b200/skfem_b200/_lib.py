@@ -50,6 +50,7 @@ SIGNATURES = {
                                   _P, _P, _P, _P, _P, _P, _P]),
     "skb_plan_rows_emit": (_INT, [_I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "skb_mesh_tensor": (_INT, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "skb_element_dofs": (_INT, [_P, _I32, _I64, _P, _P]),
     "skb_entity_masks": (_INT, [_P, _I32, _I32, _I64, _P, _P, _P, _P]),
     "skb_plan_slot_of_entry": (_INT, [_P, _P, _I64, _P, _P]),
     "skb_csr_reduce": (_INT, [_P, _P, _P, _I64, _P, _P]),

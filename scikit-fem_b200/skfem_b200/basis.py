@@ -216,7 +216,13 @@ class CellBasis(AbstractBasis):
         def up(a, dtype=None):
             a = np.ascontiguousarray(a)
             return torch.from_numpy(a).to(device)
-        d["edofs"] = t if self.element_dofs is self.mesh.t else up(self.element_dofs)
+        kept = getattr(self.dofs, "_edofs_dev", None)
+        if self.element_dofs is self.mesh.t:
+            d["edofs"] = t
+        elif kept is not None and kept[0] == key and self.element_dofs is self.dofs.element_dofs:
+            d["edofs"] = kept[1]                     # built on the device (dofs.py): no upload
+        else:
+            d["edofs"] = up(self.element_dofs)
         d["phi"], d["dphi"], d["W"], d["X"] = up(self._phi), up(self._dphi), up(self.W), up(self.X)
         d["tind"] = None if self.tind is None else up(self.tind.astype(np.int32))
         if not self._affine:

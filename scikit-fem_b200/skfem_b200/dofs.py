@@ -172,31 +172,68 @@ class Dofs:
         if element.interior_dofs == 0:      # the reference's (0, nel) table
             self.__dict__["interior_dofs"] = np.empty((0, nel), dtype=np.int32)
 
-        # nodal rows: nodal_dofs[c, v] == nd*v + c + offset0, so the gather
-        # nodal_dofs[:, t[k]] is plain integer arithmetic on t (and for one
-        # DOF per vertex element_dofs IS t: no copy, no extra upload)
+        # every row of element_dofs is  first + c + nd * entity(e)  (entity-major blocks), i.e.
+        # integer arithmetic on t / t2e / t2f; for one DOF per vertex element_dofs IS t (no
+        # copy, no extra upload)
         nd = element.nodal_dofs
         self.nodal_is_t = False
-        if nd == 1 and off0 == 0:
-            parts = [topo.t]
-            self.nodal_is_t = True
-        else:
-            parts = [np.int32(nd) * topo.t[k][None, :]
-                     + (np.arange(nd, dtype=np.int32) + np.int32(off0))[:, None]
-                     for k in range(topo.t.shape[0])] if nd > 0 else []
+        self._edofs_dev = None
+        rows = []                                   # (source, row of the source, mul, add)
+        for k in range(topo.t.shape[0]):
+            rows += [("t", k, nd, off0 + c) for c in range(nd)]
         if nedge:
-            parts += [self.edge_dofs[:, topo.t2e[k]] for k in range(topo.t2e.shape[0])]
+            for k in range(topo.t2e.shape[0]):
+                rows += [("t2e", k, nedge, self._blocks["edge_dofs"][2] + c) for c in range(nedge)]
         if element.dim >= 2 and nfac:
-            parts += [self.facet_dofs[:, topo.t2f[k]] for k in range(topo.t2f.shape[0])]
-        if element.interior_dofs:
-            parts.append(self.interior_dofs)
-        if len(parts) == 1 and self.nodal_is_t:
+            for k in range(topo.t2f.shape[0]):
+                rows += [("t2f", k, nfac, self._blocks["facet_dofs"][2] + c) for c in range(nfac)]
+        ni = element.interior_dofs
+        rows += [(None, 0, ni, self._blocks["interior_dofs"][2] + c) for c in range(ni)]
+        if nd == 1 and off0 == 0 and len(rows) == topo.t.shape[0]:
+            self.nodal_is_t = True
             self.element_dofs = topo.t
         else:
-            self.nodal_is_t = False
-            self.element_dofs = np.ascontiguousarray(np.vstack(parts), dtype=np.int32)
+            self.element_dofs = self._element_dofs_device(topo, rows)
+            if self.element_dofs is None:
+                src = {"t": topo.t, "t2e": topo.t2e if nedge else None,
+                       "t2f": topo.t2f if (element.dim >= 2 and nfac) else None}
+                e = np.arange(nel, dtype=np.int32)
+                self.element_dofs = np.ascontiguousarray(np.vstack(
+                    [np.int32(add) + np.int32(mul) * (e if s is None else src[s][r])
+                     for s, r, mul, add in rows]), dtype=np.int32)
         # == max(element_dofs) + 1: every vertex/edge/facet/cell is referenced
         self.N = int(offset + element.interior_dofs * nel)
+
+    def _element_dofs_device(self, topo, rows):
+        """element_dofs by csrc/skb_mesh.cu when the mesh (and the incidences needed) already
+        live on the GPU: the host copy comes back through pinned memory, the device copy is
+        kept for the basis (no re-upload).  None: build on the host."""
+        devs = getattr(topo, "_dev", None)
+        if not devs or topo.nelements < (1 << 16):
+            return None
+        import ctypes as C
+        import torch
+        from . import _lib
+        key, (p_dev, t_dev) = next(iter(devs.items()))
+        src = {"t": t_dev, "t2e": getattr(topo, "_t2e_dev", None),
+               "t2f": getattr(topo, "_t2f_dev", None)}
+        if any(s is not None and src[s] is None for s, _, _, _ in rows):
+            return None
+        nel = int(t_dev.shape[1])
+        desc = np.zeros(len(rows), dtype=[("src", np.int64), ("mul", np.int32), ("add", np.int32)])
+        for i, (s, r, mul, add) in enumerate(rows):
+            desc[i] = (0 if s is None else src[s][r].data_ptr(), mul, add)
+        desc_dev = torch.from_numpy(desc.view(np.uint8)).to(t_dev.device)
+        out = torch.empty((len(rows), nel), dtype=torch.int32, device=t_dev.device)
+        code = _lib.lib().skb_element_dofs(desc_dev.data_ptr(), len(rows), nel, out.data_ptr(),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(code, "skb_element_dofs")
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self._edofs_dev = (key, out)
+        self._edofs_pinned = host
+        return host.numpy()
 
     def on_facets(self, facets):
         """All DOFs attached to the vertices / edges / facets of the given facets,

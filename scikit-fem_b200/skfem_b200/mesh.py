@@ -76,7 +76,7 @@ def _edges_rows(tt, indices, nv):
     return torch.stack([rows, cols]), torch.stack(inc)
 
 
-def _build_entities_device(t, indices, nv, sort):
+def _build_entities_device(t, indices, nv, sort, keep=None):
     """``Mesh.build_entities`` on the GPU; same results as the host path,
     returned as host arrays because the numbering API is host numpy.  Edges of any mesh and the
     triangular facets of tetrahedra go through the library's own row-bucket sort (the unique
@@ -89,8 +89,11 @@ def _build_entities_device(t, indices, nv, sort):
     tt32 = torch.from_numpy(np.ascontiguousarray(t, dtype=np.int32)).to(dev)
 
     def host(ent, inc):
+        inc32 = inc.to(torch.int32).contiguous()
+        if keep is not None:
+            keep["inc"] = inc32                        # device copy for Dofs (no re-upload)
         return (np.ascontiguousarray(ent.to(torch.int32).cpu().numpy().astype(tdt, copy=False)),
-                inc.to(torch.int32).cpu().numpy().astype(np.int64))
+                inc32.cpu().numpy().astype(np.int64))
     if sort and k == 2:
         res = _edges_rows(tt32, [tuple(ix) for ix in indices], nv)
         if res is not None:
@@ -132,6 +135,8 @@ def _build_entities_device(t, indices, nv, sort):
         uhi, rhi = torch.unique(hi_key, sorted=True, return_inverse=True)
         key = (rhi * nv + canon[2]) * nv + canon[3]
         ukey, inverse = torch.unique(key, sorted=True, return_inverse=True)
+        if keep is not None:
+            keep["inc"] = inverse.reshape(len(indices), n).to(torch.int32).contiguous()
         incidence = inverse.reshape(len(indices), n).cpu().numpy()
         if not sort:
             first = torch.full((ukey.shape[0],), inverse.shape[0], dtype=torch.int64, device=dev)
@@ -154,6 +159,8 @@ def _build_entities_device(t, indices, nv, sort):
     del canon
     ukey, inverse = torch.unique(key, sorted=True, return_inverse=True)
     del key
+    if keep is not None:
+        keep["inc"] = inverse.reshape(len(indices), n).to(torch.int32).contiguous()
     incidence = inverse.reshape(len(indices), n).cpu().numpy()
     if not sort:   # representative = first occurrence, like np.unique(return_index=True)
         first = torch.full((ukey.shape[0],), inverse.shape[0], dtype=torch.int64, device=dev)
@@ -240,14 +247,15 @@ class Mesh:
 
     # -- topology --------------------------------------------------------------
     @staticmethod
-    def build_entities(t, indices, sort=True):
+    def build_entities(t, indices, sort=True, _keep=None):
         """Lower-dimensional entities as the lexicographically sorted unique
         columns of the per-element sorted vertex tuples, and the element ->
-        entity incidence."""
+        entity incidence.  ``_keep`` (dict): receives the device copy of the incidence
+        when the numbering ran on the GPU."""
         k = len(indices[0])
         nv = int(t.max()) + 1 if t.size else 1
         if t.shape[1] >= (1 << 16) and _cuda_ready():
-            res = _build_entities_device(t, indices, nv, sort)
+            res = _build_entities_device(t, indices, nv, sort, _keep)
             if res is not None:
                 return res
         if nv ** k < (1 << 62):
@@ -281,11 +289,15 @@ class Mesh:
     _sort_facets = True
 
     def _init_facets(self):
+        keep = {}
         self._facets, self._t2f = self.build_entities(self.t, self.refdom.facets,
-                                                      sort=self._sort_facets)
+                                                      sort=self._sort_facets, _keep=keep)
+        self._t2f_dev = keep.get("inc")
 
     def _init_edges(self):
-        self._edges, self._t2e = self.build_entities(self.t, self.refdom.edges)
+        keep = {}
+        self._edges, self._t2e = self.build_entities(self.t, self.refdom.edges, _keep=keep)
+        self._t2e_dev = keep.get("inc")
 
     @property
     def facets(self):
