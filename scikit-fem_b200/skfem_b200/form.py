@@ -597,7 +597,8 @@ class BilinearForm(Form):
                         from . import fused2
                         with _lib.nvtx("skfem_b200:fused"):
                             fused2.run(fp, data, _stream(),
-                                       fast=_CONFIG["fused_arith"] == "fast")
+                                       fast=_CONFIG["fused_arith"] == "fast",
+                                       l2_persist=bool(_CONFIG["fused_l2_persist"]))
                         # first run after basis.update_points: did the zero mask of any local
                         # matrix change?  Then this pattern is no longer the reference's.
                         if getattr(fp, "unchecked", False) and \
