@@ -182,10 +182,10 @@ class Dofs:
         for k in range(topo.t.shape[0]):
             rows += [("t", k, nd, off0 + c) for c in range(nd)]
         if nedge:
-            for k in range(topo.t2e.shape[0]):
+            for k in range(len(topo.refdom.edges)):       # == t2e.shape[0], without fetching it
                 rows += [("t2e", k, nedge, self._blocks["edge_dofs"][2] + c) for c in range(nedge)]
         if element.dim >= 2 and nfac:
-            for k in range(topo.t2f.shape[0]):
+            for k in range(len(topo.refdom.facets)):      # == t2f.shape[0]
                 rows += [("t2f", k, nfac, self._blocks["facet_dofs"][2] + c) for c in range(nfac)]
         ni = element.interior_dofs
         rows += [(None, 0, ni, self._blocks["interior_dofs"][2] + c) for c in range(ni)]

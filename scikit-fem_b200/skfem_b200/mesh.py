@@ -76,6 +76,12 @@ def _edges_rows(tt, indices, nv):
     return torch.stack([rows, cols]), torch.stack(inc)
 
 
+def _entities_to_host(ent32, inc32, tdt):
+    """Device entity / incidence tensors -> the host arrays of ``Mesh.build_entities``."""
+    return (np.ascontiguousarray(ent32.cpu().numpy().astype(tdt, copy=False)),
+            inc32.cpu().numpy().astype(np.int64))
+
+
 def _build_entities_device(t, indices, nv, sort, keep=None):
     """``Mesh.build_entities`` on the GPU; same results as the host path,
     returned as host arrays because the numbering API is host numpy.  Edges of any mesh and the
@@ -90,10 +96,12 @@ def _build_entities_device(t, indices, nv, sort, keep=None):
 
     def host(ent, inc):
         inc32 = inc.to(torch.int32).contiguous()
+        ent32 = ent.to(torch.int32).contiguous()
         if keep is not None:
-            keep["inc"] = inc32                        # device copy for Dofs (no re-upload)
-        return (np.ascontiguousarray(ent.to(torch.int32).cpu().numpy().astype(tdt, copy=False)),
-                inc32.cpu().numpy().astype(np.int64))
+            keep["inc"], keep["ent"] = inc32, ent32    # device copies (Dofs: no re-upload)
+            if keep.get("defer"):                      # host arrays on demand (_entities_to_host)
+                return None, None
+        return _entities_to_host(ent32, inc32, tdt)
     if sort and k == 2:
         res = _edges_rows(tt32, [tuple(ix) for ix in indices], nv)
         if res is not None:
@@ -135,14 +143,11 @@ def _build_entities_device(t, indices, nv, sort, keep=None):
         uhi, rhi = torch.unique(hi_key, sorted=True, return_inverse=True)
         key = (rhi * nv + canon[2]) * nv + canon[3]
         ukey, inverse = torch.unique(key, sorted=True, return_inverse=True)
-        if keep is not None:
-            keep["inc"] = inverse.reshape(len(indices), n).to(torch.int32).contiguous()
-        incidence = inverse.reshape(len(indices), n).cpu().numpy()
+        incidence = inverse.reshape(len(indices), n)
         if not sort:
             first = torch.full((ukey.shape[0],), inverse.shape[0], dtype=torch.int64, device=dev)
             first.scatter_reduce_(0, inverse, torch.arange(inverse.shape[0], device=dev), "amin")
-            return (np.ascontiguousarray(stacked[:, first].to(torch.int32).cpu().numpy()
-                                         .astype(tdt, copy=False)), incidence)
+            return host(stacked[:, first], incidence)
         ent = torch.empty((4, ukey.shape[0]), dtype=torch.int64, device=dev)
         ent[3] = ukey % nv
         rest = ukey // nv
@@ -150,7 +155,7 @@ def _build_entities_device(t, indices, nv, sort, keep=None):
         lead = uhi[rest // nv]
         ent[1] = lead % nv
         ent[0] = lead // nv
-        return ent.to(torch.int32).cpu().numpy().astype(tdt, copy=False), incidence
+        return host(ent, incidence)
     if float(nv) ** k >= 2.0 ** 62:
         return None                                   # keys do not pack: host path
     key = canon[0]
@@ -159,19 +164,16 @@ def _build_entities_device(t, indices, nv, sort, keep=None):
     del canon
     ukey, inverse = torch.unique(key, sorted=True, return_inverse=True)
     del key
-    if keep is not None:
-        keep["inc"] = inverse.reshape(len(indices), n).to(torch.int32).contiguous()
-    incidence = inverse.reshape(len(indices), n).cpu().numpy()
+    incidence = inverse.reshape(len(indices), n)
     if not sort:   # representative = first occurrence, like np.unique(return_index=True)
         first = torch.full((ukey.shape[0],), inverse.shape[0], dtype=torch.int64, device=dev)
         first.scatter_reduce_(0, inverse, torch.arange(inverse.shape[0], device=dev), "amin")
-        return (np.ascontiguousarray(stacked[:, first].to(torch.int32).cpu().numpy()
-                                     .astype(tdt, copy=False)), incidence)
+        return host(stacked[:, first], incidence)
     ent = torch.empty((k, ukey.shape[0]), dtype=torch.int64, device=dev)
     for r in range(k - 1, -1, -1):
         ent[r] = ukey % nv
         ukey = ukey // nv
-    return ent.to(torch.int32).cpu().numpy().astype(tdt, copy=False), incidence
+    return host(ent, incidence)
 
 
 class Mesh:
@@ -231,15 +233,24 @@ class Mesh:
     def nnodes(self):
         return self.t.shape[0]
 
+    def _nentities(self, what):
+        names = {"facets": "_facets", "edges": "_edges"}[what]
+        if not hasattr(self, names) and not hasattr(self, names + "_dev"):
+            self._init_entities(what, getattr(self.refdom, what),
+                                self._sort_facets if what == "facets" else True)
+        if hasattr(self, names):
+            return getattr(self, names).shape[1]
+        return int(getattr(self, names + "_dev").shape[1])
+
     @property
     def nfacets(self):
-        return self.facets.shape[1]
+        return self._nentities("facets")
 
     @property
     def nedges(self):
         if self.refdom.edges is None:
             raise NotImplementedError
-        return self.edges.shape[1]
+        return self._nentities("edges")
 
     def __repr__(self):
         return "<skfem_b200 {} object>\n  Number of elements: {}\n  Number of vertices: {}".format(
@@ -288,16 +299,38 @@ class Mesh:
 
     _sort_facets = True
 
+    # Entities numbered on the GPU stay there (``_facets_dev`` / ``_t2f_dev`` ...: Dofs builds
+    # element_dofs from them without a round trip); the host arrays of the public attributes
+    # are fetched on first access.
+    def _init_entities(self, what, indices, sort):
+        keep = {"defer": True}
+        ent, inc = self.build_entities(self.t, indices, sort=sort, _keep=keep)
+        names = {"facets": ("_facets", "_t2f"), "edges": ("_edges", "_t2e")}[what]
+        if ent is None:                               # deferred: device tensors only
+            setattr(self, names[0] + "_dev", keep["ent"])
+            setattr(self, names[1] + "_dev", keep["inc"])
+        else:
+            setattr(self, names[0], ent)
+            setattr(self, names[1], inc)
+            setattr(self, names[1] + "_dev", keep.get("inc"))
+
+    def _host_entities(self, what):
+        names = {"facets": ("_facets", "_t2f"), "edges": ("_edges", "_t2e")}[what]
+        if not hasattr(self, names[0]):
+            if not hasattr(self, names[0] + "_dev"):
+                self._init_entities(what, getattr(self.refdom, what),
+                                    self._sort_facets if what == "facets" else True)
+            if not hasattr(self, names[0]):
+                ent, inc = _entities_to_host(getattr(self, names[0] + "_dev"),
+                                             getattr(self, names[1] + "_dev"), self.t.dtype)
+                setattr(self, names[0], ent)
+                setattr(self, names[1], inc)
+
     def _init_facets(self):
-        keep = {}
-        self._facets, self._t2f = self.build_entities(self.t, self.refdom.facets,
-                                                      sort=self._sort_facets, _keep=keep)
-        self._t2f_dev = keep.get("inc")
+        self._host_entities("facets")
 
     def _init_edges(self):
-        keep = {}
-        self._edges, self._t2e = self.build_entities(self.t, self.refdom.edges, _keep=keep)
-        self._t2e_dev = keep.get("inc")
+        self._host_entities("edges")
 
     @property
     def facets(self):
@@ -384,7 +417,8 @@ class Mesh:
                            if callable(spec) else np.asarray(spec, dtype=np.int32))
         out.boundaries = named
         out.subdomains = self.subdomains
-        for attr in ("_facets", "_t2f", "_edges", "_t2e", "_f2t", "_nvertices"):
+        for attr in ("_facets", "_t2f", "_edges", "_t2e", "_f2t", "_nvertices", "_facets_dev",
+                     "_t2f_dev", "_edges_dev", "_t2e_dev"):
             if hasattr(self, attr):
                 setattr(out, attr, getattr(self, attr))
         return out
