@@ -48,6 +48,7 @@ from . import _lib
 from .fused import FusedPlanTooBig, _kd_order  # noqa: F401  (same exceptions / tiling)
 
 NONE = 0xFFFFFFFF
+L2_WINDOW_MAX_BYTES = 40 << 20
 POOL_MAX = 8192          # 13-bit pool index
 
 
@@ -509,7 +510,10 @@ def run(fp, data, stream, fast=False, p=None, l2_persist=True):
     # the partials of the shared slots are written once by the fused kernel and read once by the
     # combine kernel right after it: an L2 persisting window keeps that round trip out of HBM
     # (measured -1.2 % of the step; the same window on the vertex coordinates costs +1.2 %)
-    persist = l2_persist and fp.nscratch > 0
+    # ... as long as the partials are a small part of the 126 MB L2: a window over hundreds of
+    # MB (the 47 M-element parts of BASELINE configs[4] on 2 GPUs: 236 MB) sets most of the L2
+    # aside and starves the streamed records - measured 2.86 instead of 1.47 ms per step
+    persist = l2_persist and 0 < 8 * fp.nscratch <= L2_WINDOW_MAX_BYTES
     if persist:
         _lib.check(lib.skb_l2_window(fp.scratch.data_ptr(), 8 * fp.nscratch, stream),
                    "skb_l2_window")
