@@ -22,14 +22,16 @@ F.set_options(plan_method="rows")
 laplace.assemble_device(b1)                # fused plan build + fused kernel + combine
 laplace.assemble_device(b1)
 unit_load.assemble_device(b1)              # local_linear, vec_reduce
+mass.assemble_device(b1)                   # sym kernel; then the fused mass path (MODE 4)
 mass.assemble_device(b1)
-xs = np.linspace(0, 1, (n + 1) // 2)
+mass.assemble_device(b1)
+xs = np.linspace(0, 1, max((n + 1) // 2, 25))   # >= 65 536 tets: entities / DOF tables on the GPU
 ms = fem.MeshTet.init_tensor(xs, xs, xs)
 b2 = fem.Basis(ms, fem.ElementTetP2())
 laplace.assemble_device(b2)
 bv = fem.Basis(ms, fem.ElementVector(fem.ElementTetP2()))
 linear_elasticity(*lame_parameters(1e3, 0.3)).assemble_device(bv)   # cached vector kernel
-xh = np.linspace(0, 1, (n + 1) // 2)
+xh = np.linspace(0, 1, max((n + 1) // 2, 42))   # >= 65 536 hexes
 mh = fem.MeshHex.init_tensor(xh, xh, xh)
 laplace.assemble_device(fem.Basis(mh, fem.ElementHex1()))           # local_hex
 bh2 = fem.Basis(mh, fem.ElementHex2())
