@@ -265,7 +265,8 @@ def apply_options(args):
                       fused_renumber=not args.no_renumber, fused_tiling=args.tiling,
                       fused_version=args.fused_version, fused2_tile=args.tile2,
                       fused2_ring=args.ring2, fused2_pool=args.pool, fused2_ctas=args.ctas,
-                      fused2_S=args.super_tiles, fused2_ept=args.ept)
+                      fused2_S=args.super_tiles, fused2_ept=args.ept,
+                      hex_sumfact=not args.no_hex_sumfact)
     return _form
 
 
@@ -761,6 +762,8 @@ def main():
                     help="profiling aid (skb_debug_flags): 1 skip P1, 2 skip P2; invalid results")
     ap.add_argument("--no-graph", action="store_true", dest="no_graph",
                     help="launch the warm step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-hex-sumfact", action="store_true", dest="no_hex_sumfact",
+                    help="config c4: the Gram-matrix tensor-core kernel instead of sum factorisation")
     ap.add_argument("--no-fused", action="store_true", dest="no_fused",
                     help="time the generic two-kernel path instead of the fused P1 kernel")
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"],

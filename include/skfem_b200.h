@@ -85,6 +85,22 @@ int skb_local_bilinear(const skb_space_t *space, int form, const double *params_
 int skb_local_linear(const skb_space_t *space, int form, const double *params_host,
                      double *out_local, void *stream);
 
+/* ElementHex2 (27 functions) on trilinear hexahedra at the default 7^3 tensor rule, laplace |
+ * mass (models/poisson.py:7-19 over element_hex2.py:1255-1260, mapping_isoparametric.py:
+ * 112-226, quadrature.py:63-77): the same element-local data as skb_local_bilinear, computed
+ * by sum factorisation (csrc/skb_hex_sf.cu) - one axis of the tensor-product rule at a time,
+ * 63 k instead of 750 k multiply-adds per element.  Value-level parity (rtol 1e-12).  Host
+ * tables: qstride[3] stride of each axis' 1-D index in the point index of `space`;
+ * pp[4][9][nq] products of the 1-D quadratic functions (type bit 0 / 1: derivative on the
+ * first / second factor; row 3 i + j; nodes 0, 1/2, 1); g[2][nq] = 1 - x, x; bnode[27] =
+ * a + 3 b + 9 c (1-D node of each basis function per axis); vtx[8] local vertex at corner
+ * 4 a + 2 b + c.  Returns SKB_EINVAL for anything but nq = 7 / 27 functions (callers then use
+ * skb_local_bilinear), SKB_EZERODET like the reference raises (synchronises the stream).    */
+int skb_local_hex_sumfact(const skb_space_t *space, int form, int32_t nq,
+                          const int32_t *qstride_host, const double *pp_host,
+                          const double *g_host, const uint8_t *bnode_host,
+                          const uint8_t *vtx_host, double *out_local, void *stream);
+
 /* ---- sparsity plan: replaces COOData._assemble_scipy_csr's structure ----
  * (assembly/form/coo_data.py:27-36 -> scipy coo_matrix.eliminate_zeros +
  * tocsr: coo_tocsr, csr_sort_indices, csr_sum_duplicates).

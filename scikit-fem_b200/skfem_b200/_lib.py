@@ -39,6 +39,8 @@ _PD = C.POINTER(C.c_double)
 SIGNATURES = {
     "skb_local_bilinear": (_INT, [_SP, _INT, _PD, _P, _P]),
     "skb_local_linear": (_INT, [_SP, _INT, _PD, _P, _P]),
+    "skb_local_hex_sumfact": (_INT, [_SP, _INT, _I32, C.POINTER(C.c_int32), _PD, _PD,
+                                     C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _P, _P]),
     "skb_plan_scratch_bytes": (_I64, [_I64]),
     "skb_plan_symbolic": (_INT, [_P, _P, _I32, _I32, _I64, _I64, _I64, _P, _INT,
                                  _P, _P, _P, _P, _P, _P, _I64, C.POINTER(_I64), _P]),

@@ -34,6 +34,7 @@ from typing import Any, Optional, Tuple
 import numpy as np
 
 from . import _lib
+from . import hex_sumfact as _hex_sumfact
 from .field import DeviceArray, DiscreteField, combine_layout, layout_of
 
 logger = logging.getLogger(__name__)
@@ -61,6 +62,8 @@ def _torch():
 #                     fused_tile elements; "kd": compact boxes from a balanced k-d tree
 #                     (fused._kd_order; fewer CSR slots shared between tiles - plan-only
 #                     change, not yet timed on a B200, hence opt-in)
+#   hex_sumfact      ElementHex2 laplace / mass at the default rule by sum factorisation
+#                     (csrc/skb_hex_sf.cu); False: the Gram-matrix tensor-core kernel
 #   fused_version    2: super-tile / pool kernel (csrc/skb_p1_fused2.cu, fused2.py; options
 #                     fused2_tile, fused2_ring, fused2_pool, fused2_ctas, fused2_S);
 #                     1: the first-generation warp-specialised kernel (options above)
@@ -68,7 +71,8 @@ _CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring":
            "fused_arith": "exact", "fused_spread": True, "fused_renumber": True,
            "fused_l2_persist": True, "fused_tiling": "morton",
            "fused_version": 2, "fused2_tile": 256, "fused2_ring": 3, "fused2_pool": 2048,
-           "fused2_ctas": 0, "fused2_S": None, "fused2_ept": 1, "plan_method": "rows"}
+           "fused2_ctas": 0, "fused2_S": None, "fused2_ept": 1, "plan_method": "rows",
+           "hex_sumfact": True}
 
 
 def set_options(**kw):
@@ -520,6 +524,14 @@ class BilinearForm(Form):
         if self._native_applicable(ubasis, vbasis if vbasis is not ubasis else None, kwargs):
             _, kid, params, _ = self.native
             cparams = None if params is None else (C.c_double * len(params))(*params)
+            if kid in (_lib.FORM_LAPLACE, _lib.FORM_MASS) and _CONFIG["hex_sumfact"]:
+                # ElementHex2 at its default rule: sum factorisation (csrc/skb_hex_sf.cu)
+                tab = _hex_sumfact.tables(ubasis)
+                if tab is not None:
+                    code = _hex_sumfact.launch(_lib.lib(), d["space"], kid, tab,
+                                               out.data_ptr(), _stream())
+                    _lib.check(code, "skb_local_hex_sumfact")
+                    return out
             code = _lib.lib().skb_local_bilinear(C.byref(d["space"]), kid, cparams,
                                                  out.data_ptr(), _stream())
             _lib.check(code, "skb_local_bilinear")

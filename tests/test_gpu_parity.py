@@ -49,33 +49,73 @@ def test_against_reference_golden(name):
             assert np.array_equal(vec, g[f + "_vec"]), (name, f)
 
 
+@pytest.mark.parametrize("sumfact", [True, False])
 @pytest.mark.parametrize("name", ["hex2_tensor2", "hex2_morphed2", "hex2_morphed4"])
-def test_hex2_value_parity(name):
-    """Hex2 with the reference's own tables (shipped for the default rule): the FP64
-    tensor-core (Gram) kernel re-orders the quadrature sum, so parity is value-level - at the
-    north-star tolerance rtol 1e-12 - with a bit-exact pattern; the scalar kernel
-    (skb_debug_flags(8)) follows the reference's order and reproduces its element-local data
-    bit for bit."""
-    from skfem_b200 import _lib
+def test_hex2_value_parity(name, sumfact):
+    """Hex2 at the default rule: the sum-factorised kernel (csrc/skb_hex_sf.cu) and the FP64
+    tensor-core Gram kernel behind it (csrc/skb_hex_mma.cu, with the reference's own tables)
+    both re-associate the quadrature sum, so parity is value-level - at the north-star
+    tolerance rtol 1e-12 - with a bit-exact pattern; the scalar kernel (skb_debug_flags(8))
+    follows the reference's order and reproduces its element-local data bit for bit."""
+    from skfem_b200 import _lib, form as F
     g = load(name)
     b = fem.Basis(mesh_from(g, "hex"), fem.ElementHex2())
     assert np.array_equal(b.element_dofs, g["element_dofs"])
     fs = forms(False)
-    for f in ["laplace", "mass"]:
-        A = fs[f].assemble(b)
-        assert np.array_equal(A.indptr, g[f + "_indptr"])
-        assert np.array_equal(A.indices, g[f + "_indices"])
-        ref = g[f + "_data"]
-        np.testing.assert_allclose(A.data, ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
-        if f + "_local" in g.files:
-            loc = g[f + "_local"]
-            got = fs[f].elemental(b).data
-            np.testing.assert_allclose(got, loc, rtol=RTOL, atol=RTOL * np.abs(loc).max())
+    F.set_options(hex_sumfact=sumfact)
+    try:
+        for f in ["laplace", "mass"]:
+            A = fs[f].assemble(b)
+            assert np.array_equal(A.indptr, g[f + "_indptr"])
+            assert np.array_equal(A.indices, g[f + "_indices"])
+            ref = g[f + "_data"]
+            np.testing.assert_allclose(A.data, ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
+            if f + "_local" in g.files:
+                loc = g[f + "_local"]
+                got = fs[f].elemental(b).data
+                np.testing.assert_allclose(got, loc, rtol=RTOL, atol=RTOL * np.abs(loc).max())
+                if not sumfact:
+                    try:
+                        _lib.lib().skb_debug_flags(8)           # scalar kernel, reference order
+                        assert np.array_equal(fs[f].elemental(b).data, loc), f
+                    finally:
+                        _lib.lib().skb_debug_flags(0)
+    finally:
+        F.set_options(hex_sumfact=True)
+
+
+def test_hex2_sumfact_ragged_batches_subsets_and_zero_jacobian():
+    """27 elements (the kernel takes 4 per CTA pass: the last pass is ragged), an element
+    subset, and a collapsed element: the sum-factorised kernel against the Gram kernel."""
+    from skfem_b200 import form as F
+    from skfem_b200.models.poisson import laplace, mass
+    x = np.linspace(0, 1, 4) ** 1.3
+    m = fem.MeshHex.init_tensor(x, np.linspace(0, 2, 4), x)
+    p = m.p.copy()
+    p += 0.02 * np.sin(7 * p[[1, 2, 0]])                 # trilinear, non-affine cells
+    m = fem.MeshHex(p, m.t)
+    for elements in (None, np.array([0, 5, 6, 13, 20, 26])):
+        out = {}
+        for sf in (True, False):
+            F.set_options(hex_sumfact=sf)
             try:
-                _lib.lib().skb_debug_flags(8)           # scalar kernel, reference order
-                assert np.array_equal(fs[f].elemental(b).data, loc), f
+                b = fem.Basis(m, fem.ElementHex2(), elements=elements)
+                out[sf] = [laplace.elemental(b).data, mass.elemental(b).data,
+                           laplace.assemble(b), mass.assemble(b)]
             finally:
-                _lib.lib().skb_debug_flags(0)
+                F.set_options(hex_sumfact=True)
+        for a, c in zip(out[True][:2], out[False][:2]):
+            np.testing.assert_allclose(a, c, rtol=RTOL, atol=RTOL * np.abs(c).max())
+            assert not np.array_equal(a, c)               # really two different kernels
+        for A, B in zip(out[True][2:], out[False][2:]):
+            assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+            np.testing.assert_allclose(A.data, B.data, rtol=RTOL, atol=RTOL * np.abs(B.data).max())
+    # mapping_isoparametric.py:195-196: a cell squeezed to zero volume raises
+    p2 = p.copy()
+    p2[2, m.t[:, 3]] = p2[2, m.t[0, 3]]
+    b = fem.Basis(fem.MeshHex(p2, m.t), fem.ElementHex2())
+    with pytest.raises(Exception, match="Zero Jacobian determinant"):
+        laplace.elemental(b)
 
 
 def test_known_answers():
