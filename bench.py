@@ -266,7 +266,8 @@ def apply_options(args):
                       fused_version=args.fused_version, fused2_tile=args.tile2,
                       fused2_ring=args.ring2, fused2_pool=args.pool, fused2_ctas=args.ctas,
                       fused2_S=args.super_tiles, fused2_ept=args.ept,
-                      hex_sumfact=not args.no_hex_sumfact)
+                      hex_sumfact=not args.no_hex_sumfact,
+                      element_major=not args.no_element_major)
     return _form
 
 
@@ -623,6 +624,8 @@ def run_config(args):
     import skfem_b200 as fem
     from skfem_b200 import _lib
     apply_options(args)
+    if args.debug_flags:
+        _lib.lib().skb_debug_flags(args.debug_flags)   # kernel variants (A/B runs)
     name = args.config
     npts = args.cells + 1 if args.cells != 100 else CONFIGS[name][1]
     m, elem, form = build_config(name, npts, fem)
@@ -764,6 +767,8 @@ def main():
                     help="launch the warm step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-hex-sumfact", action="store_true", dest="no_hex_sumfact",
                     help="config c4: the Gram-matrix tensor-core kernel instead of sum factorisation")
+    ap.add_argument("--no-element-major", action="store_true", dest="no_element_major",
+                    help="config c4: local data in the reference layout (Nb, Nb, nel) on warm calls")
     ap.add_argument("--no-fused", action="store_true", dest="no_fused",
                     help="time the generic two-kernel path instead of the fused P1 kernel")
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"],

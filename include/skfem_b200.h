@@ -95,11 +95,15 @@ int skb_local_linear(const skb_space_t *space, int form, const double *params_ho
  * first / second factor; row 3 i + j; nodes 0, 1/2, 1); g[2][nq] = 1 - x, x; bnode[27] =
  * a + 3 b + 9 c (1-D node of each basis function per axis); vtx[8] local vertex at corner
  * 4 a + 2 b + c.  Returns SKB_EINVAL for anything but nq = 7 / 27 functions (callers then use
- * skb_local_bilinear), SKB_EZERODET like the reference raises (synchronises the stream).    */
+ * skb_local_bilinear), SKB_EZERODET like the reference raises (synchronises the stream).
+ * element_major != 0: out_local is written as (nel, Nbv, Nbu) instead - 729 consecutive values
+ * per element, the layout skb_csr_reduce_em gathers from (warm re-assembly; the plan builders
+ * and COOData read the reference layout).                                                   */
 int skb_local_hex_sumfact(const skb_space_t *space, int form, int32_t nq,
                           const int32_t *qstride_host, const double *pp_host,
                           const double *g_host, const uint8_t *bnode_host,
-                          const uint8_t *vtx_host, double *out_local, void *stream);
+                          const uint8_t *vtx_host, int32_t element_major, double *out_local,
+                          void *stream);
 
 /* ---- sparsity plan: replaces COOData._assemble_scipy_csr's structure ----
  * (assembly/form/coo_data.py:27-36 -> scipy coo_matrix.eliminate_zeros +
@@ -191,6 +195,13 @@ int skb_plan_slot_of_entry(const uint32_t *segptr, const uint32_t *perm, int64_t
  * sequentially in that fixed order: deterministic, no float atomics.       */
 int skb_csr_reduce(const double *local, const uint32_t *perm, const uint32_t *segptr,
                    int64_t nnz, double *data, void *stream);
+/* The same sums, in the same order, over element-major local data local_em (nel, Nbv, Nbu):
+ * COO entry k = (j*Nbv + i)*nel + e is read at e*Nbu*Nbv + i*Nbu + j, so the entries a CSR
+ * row takes from one element are consecutive in memory (whole 32-byte sectors are used; in
+ * the reference layout they are nel doubles apart).  perm / segptr are the plan's, unchanged. */
+int skb_csr_reduce_em(const double *local_em, int64_t nel, int32_t nbu, int32_t nbv,
+                      const uint32_t *perm, const uint32_t *segptr, int64_t nnz, double *data,
+                      void *stream);
 /* LinearForm scatter, replaces COOData.toarray 1-tensor branch / scipy
  * coo_todense (coo_data.py:102-108): vec[r] = sequential sum in COO order. */
 int skb_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *segptr,

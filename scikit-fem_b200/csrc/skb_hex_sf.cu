@@ -66,71 +66,86 @@ template <int FORM> struct SfShape {
   static constexpr int R0 = SZ_G > SZ_T2 ? SZ_G : SZ_T2;                   // G, then T2
   static constexpr int R1a = SZ_T1 > SZ_B ? SZ_T1 : SZ_B;
   static constexpr int R1 = R1a > SZ_JC ? R1a : SZ_JC;                     // J columns, T1, B
-  static constexpr int PER = R0 + R1 + 24;                                 // + vertex coordinates
+  static constexpr int PER = R0 + R1;
 };
+// per-element stride: == 16 / E (mod 16) doubles, so that the E elements a warp of the last
+// stage reads side by side sit in different 8-byte banks
+template <int FORM, int E> __host__ __device__ constexpr int sf_per() {
+  constexpr int want = (16 / E) % 16, have = SfShape<FORM>::PER % 16;
+  return SfShape<FORM>::PER + (want - have + 16) % 16;
+}
 
-template <int FORM, int E, int T>
-__global__ void __launch_bounds__(T, 1)
-local_hex_sf_kernel(const skb_space_t s, const __grid_constant__ HexSfTab tb,
+template <int FORM, int E, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB)
+local_hex_sf_kernel(const skb_space_t s, const __grid_constant__ HexSfTab tb, const int em,
                     double *__restrict__ out, int *__restrict__ err) {
   using S = SfShape<FORM>;
   constexpr int NQ = S::NQ, NQ2 = S::NQ2, NQ3 = S::NQ3, NC = S::NC, NG = S::NG;
   constexpr int LD1 = S::LD1, LD2 = S::LD2;
   constexpr bool LAP = FORM == SKB_FORM_LAPLACE;
+  static_assert(E * 36 <= T && T % E == 0, "one edge difference per thread");
   extern __shared__ double sm[];
   __shared__ double sg[2][NQ];
-  __shared__ int sbn[27][3];
-  __shared__ int svtx[8];
+  __shared__ double sd[E * 36];          // edge differences [el][f][2 a + b][i] of the batch
+  __shared__ uint16_t sinv[730];         // 27 i + j of the B entry (i1 j1, i2 j2, i3 j3)
   const int tid = threadIdx.x;
   if (tid < 2 * NQ) sg[tid / NQ][tid % NQ] = tb.g[tid / NQ][tid % NQ];
-  if (tid < 27) {
-    const int b = tb.bnode[tid];
-    sbn[tid][0] = b % 3, sbn[tid][1] = (b / 3) % 3, sbn[tid][2] = b / 9;
+  for (int ij = tid; ij < 729; ij += T) {
+    const int bi = tb.bnode[ij / 27], bj = tb.bnode[ij % 27];
+    const int i1 = bi % 3, i2 = (bi / 3) % 3, i3 = bi / 9, j1 = bj % 3, j2 = (bj / 3) % 3,
+              j3 = bj / 9;
+    sinv[((i1 * 3 + j1) * 9 + i2 * 3 + j2) * 9 + i3 * 3 + j3] = (uint16_t)ij;
   }
-  if (tid < 8) svtx[tid] = tb.vtx[tid];
-  const int nbs = s.nbs;                                  // 27
-  auto r0 = [&](int el) { return sm + el * S::PER; };
-  auto r1 = [&](int el) { return sm + el * S::PER + S::R0; };
-  auto xn = [&](int el) { return sm + el * S::PER + S::R0 + S::R1; };
+  constexpr int PER = sf_per<FORM, E>();
+  auto r0 = [&](int el) { return sm + el * PER; };
+  auto r1 = [&](int el) { return sm + el * PER + S::R0; };
+  // thread tid < 36 E owns one component of one edge difference of the trilinear map:
+  // x(f = 1, a, b) - x(f = 0, a, b), (a, b) the corner bits of the two other axes.  The two
+  // dependent loads (vertex numbers, coordinates) of the next pass are issued at different
+  // points of the current one, so that neither latency is waited for
+  int vhi = 0, vlo = 0;
+  auto load_verts = [&](int64_t b0) {
+    if (tid >= E * 36 || b0 >= s.nel) return;
+    const int el = tid / 36, r = tid % 36, f = r / 12, a = (r / 6) & 1, b = (r / 3) & 1;
+    const int wf = 4 >> f, wu = f == 0 ? 2 : 4, wv = f == 2 ? 2 : 1;     // corner bit weights
+    int64_t e = b0 + el;
+    if (e >= s.nel) e = s.nel - 1;                        // slots past the end repeat the last
+    const int64_t eg = s.tind ? (int64_t)s.tind[e] : e;
+    vlo = s.t[(int64_t)tb.vtx[a * wu + b * wv] * s.nel_total + eg];
+    vhi = s.t[(int64_t)tb.vtx[wf + a * wu + b * wv] * s.nel_total + eg];
+  };
+  auto load_diff = [&]() -> double {
+    const double *pi = s.p + (int64_t)(tid % 3) * s.npts;   // component i = (tid % 36) % 3
+    return tid < E * 36 ? __ldg(pi + vhi) - __ldg(pi + vlo) : 0.0;
+  };
+  load_verts((int64_t)blockIdx.x * E);
+  double dnext = load_diff();
 
   for (int64_t base = (int64_t)blockIdx.x * E; base < s.nel; base += (int64_t)gridDim.x * E) {
-    // ---- vertex coordinates of the E elements (slots past the end repeat the last one) ---
-    for (int idx = tid; idx < E * 24; idx += T) {
-      const int el = idx / 24, r = idx % 24, v = r / 3, i = r % 3;
-      int64_t e = base + el;
-      if (e >= s.nel) e = s.nel - 1;
-      const int64_t eg = s.tind ? (int64_t)s.tind[e] : e;
-      const int64_t vert = s.t[(int64_t)v * s.nel_total + eg];
-      xn(el)[v * 3 + i] = __ldg(s.p + (int64_t)i * s.npts + vert);
-    }
-    __syncthreads();
+    if (tid < E * 36) sd[tid] = dnext;
+    __syncthreads();           // also: the previous pass' reads of B are over (J columns alias it)
     // ---- Jacobian columns: column f depends on the two other axes only -------------------
-    // Jc[f][i][qu qv] = sum_{s,t} (x(f = 1, s, t) - x(f = 0, s, t))_i g_s(qu) g_t(qv)
+    // Jc[f][i][qu qv] = sum_{a,b} (x(f = 1, a, b) - x(f = 0, a, b))_i g_a(qu) g_b(qv)
     for (int item = tid; item < E * 3 * NQ2; item += T) {
       const int el = item / (3 * NQ2), r = item % (3 * NQ2), f = r / NQ2, uv = r % NQ2;
       const int qu = uv / NQ, qv = uv % NQ;
-      const int wf = 4 >> f, wu = f == 0 ? 2 : 4, wv = f == 2 ? 2 : 1;   // corner bit weights
-      const double *x = xn(el);
-      double acc[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const double w = sg[a][qu] * sg[b][qv];
-          const int hi = svtx[wf + a * wu + b * wv], lo = svtx[a * wu + b * wv];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) acc[i] = __fma_rn(x[hi * 3 + i] - x[lo * 3 + i], w, acc[i]);
-        }
+      const double *d = sd + el * 36 + f * 12;
+      const double gu0 = sg[0][qu], gu1 = sg[1][qu], gv0 = sg[0][qv], gv1 = sg[1][qv];
+      const double w00 = gu0 * gv0, w01 = gu0 * gv1, w10 = gu1 * gv0, w11 = gu1 * gv1;
       double *jc = r1(el);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) jc[(f * 3 + i) * NQ2 + uv] = acc[i];
+      for (int i = 0; i < 3; ++i)
+        jc[(f * 3 + i) * NQ2 + uv] =
+            __fma_rn(d[9 + i], w11, __fma_rn(d[6 + i], w10, __fma_rn(d[3 + i], w01, d[i] * w00)));
     }
     __syncthreads();
+    load_verts(base + (int64_t)gridDim.x * E);             // in flight during the G stage
     // ---- G at every point ----------------------------------------------------------------
+#pragma unroll 2
     for (int item = tid; item < E * NQ3; item += T) {
       const int el = item / NQ3, q = item % NQ3, q1 = q / NQ2, q2 = (q / NQ) % NQ, q3 = q % NQ;
       const double *jc = r1(el);
-      double J[3][3], nn[3][3];
+      double J[3][3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         J[i][0] = jc[(0 + i) * NQ2 + q2 * NQ + q3];
@@ -142,8 +157,18 @@ local_hex_sf_kernel(const skb_space_t s, const __grid_constant__ HexSfTab tb,
       const double w = __ldg(s.W + q1 * tb.qs[0] + q2 * tb.qs[1] + q3 * tb.qs[2]);
       double *G = r0(el);
       if (LAP) {
-        cofactors3(J, nn);                              // nn / det = J^-1
-        const double sc = w / fabs(det);
+        double nn[3][3];                                // adjugate: nn / det = J^-1
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int r1_ = (r + 1) % 3, r2_ = (r + 2) % 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+            // cofactor of J[c][r] (cyclic form, no sign flips)
+            nn[r][c] = __fma_rn(J[c1][r1_], J[c2][r2_], -(J[c1][r2_] * J[c2][r1_]));
+          }
+        }
+        const double sc = w * __drcp_rn(fabs(det));
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int d = sf_d(c), e = sf_e(c);
@@ -154,6 +179,7 @@ local_hex_sf_kernel(const skb_space_t s, const __grid_constant__ HexSfTab tb,
         G[q] = fabs(det) * w;
       }
     }
+    dnext = load_diff();                                   // in flight during stages 1 - 3
     __syncthreads();
     // ---- stage 1: contract q1 ---------------------------------------------------------------
     for (int item = tid; item < E * NQ2; item += T) {
@@ -224,46 +250,55 @@ local_hex_sf_kernel(const skb_space_t s, const __grid_constant__ HexSfTab tb,
 #pragma unroll
           for (int q = 0; q < NQ; ++q) acc[h][k] = __fma_rn(tq[q], tb.pp[ty][k][q], acc[h][k]);
       }
+      // stored at the position of the output entry (27 i + j): the last stage then reads
+      // consecutive values (and a stride-27 transpose), both free of bank conflicts
 #pragma unroll
-      for (int h = 0; h < S::NB; ++h)
+      for (int k = 0; k < 9; ++k) {
+        const int pos = sinv[ab * 9 + k];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) B[h * 729 + ab * 9 + k] = acc[h][k];
+        for (int h = 0; h < S::NB; ++h) B[h * 729 + pos] = acc[h][k];
+      }
     }
     __syncthreads();
     // ---- A_ij = Bsym_ij + (Boff_ij + Boff_ji), E consecutive elements per (i, j) ---------------
-    for (int item = tid; item < E * 729; item += T) {
-      const int ij = item / E, el = item % E, i = ij / 27, j = ij % 27;
-      if (base + el >= s.nel) continue;
-      const double *B = r1(el);
-      const int x1 = ((sbn[i][0] * 3 + sbn[j][0]) * 9 + sbn[i][1] * 3 + sbn[j][1]) * 9 +
-                     sbn[i][2] * 3 + sbn[j][2];
-      double v = B[x1];
-      if (LAP) {
-        const int x2 = ((sbn[j][0] * 3 + sbn[i][0]) * 9 + sbn[j][1] * 3 + sbn[i][1]) * 9 +
-                       sbn[j][2] * 3 + sbn[i][2];
-        v = v + (B[729 + x1] + B[729 + x2]);
+    if (em) {
+      // element-major output (nel, 27, 27): 729 consecutive values per element
+      for (int item = tid; item < E * 729; item += T) {
+        const int el = item / 729, ij = item % 729;
+        if (base + el >= s.nel) break;
+        const double *B = r1(el);
+        double v = B[ij];
+        if (LAP) v = v + (B[729 + ij] + B[729 + (ij % 27) * 27 + ij / 27]);
+        out[(base + el) * 729 + ij] = v;
       }
-      out[((int64_t)i * nbs + j) * s.nel + base + el] = v;
+    } else if (base + tid % E < s.nel) {                  // T % E == 0: el is fixed per thread
+      const double *B = r1(tid % E);
+      double *o = out + base + tid % E;
+#pragma unroll 4
+      for (int ij = tid / E; ij < 729; ij += T / E) {
+        double v = B[ij];
+        if (LAP) v = v + (B[729 + ij] + B[729 + (ij % 27) * 27 + ij / 27]);
+        o[(int64_t)ij * s.nel] = v;                       // ij = 27 i + j
+      }
     }
-    // the next iteration's first barrier orders these reads of B before the J columns are
-    // written over them
+    // the next pass' first barrier orders these reads of B before the J columns are written
+    // over them
   }
 }
 
 // launched by skb_local_hex_sumfact; `err` is the device zero-determinant flag
-template <int FORM>
-static int launch_hex_sf(const skb_space_t &s, const HexSfTab &tb, double *out, int *err,
+template <int FORM, int E, int T, int MINB>
+static int launch_hex_sf(const skb_space_t &s, const HexSfTab &tb, int em, double *out, int *err,
                          cudaStream_t st) {
-  constexpr int E = 4, T = 256;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = sizeof(double) * (size_t)E * SfShape<FORM>::PER;
-  auto k = local_hex_sf_kernel<FORM, E, T>;
+  const size_t smem = sizeof(double) * (size_t)E * sf_per<FORM, E>();
+  auto k = local_hex_sf_kernel<FORM, E, T, MINB>;
   SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t need = (s.nel + E - 1) / E;
-  const int grid = (int)(need < sms ? need : sms);
-  k<<<grid, T, smem, st>>>(s, tb, out, err);
+  const int64_t need = (s.nel + E - 1) / E, cap = (int64_t)sms * MINB;
+  const int grid = (int)(need < cap ? need : cap);
+  k<<<grid, T, smem, st>>>(s, tb, em, out, err);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -273,8 +308,10 @@ static int launch_hex_sf(const skb_space_t &s, const HexSfTab &tb, double *out, 
 extern "C" int skb_local_hex_sumfact(const skb_space_t *space, int form, int32_t nq,
                                      const int32_t *qstride_host, const double *pp_host,
                                      const double *g_host, const uint8_t *bnode_host,
-                                     const uint8_t *vtx_host, double *out_local, void *stream) {
+                                     const uint8_t *vtx_host, int32_t element_major,
+                                     double *out_local, void *stream) {
   using namespace skb;
+  const int em = element_major != 0;
   if (!space || !qstride_host || !pp_host || !g_host || !bnode_host || !vtx_host || !out_local)
     return SKB_EINVAL;
   const skb_space_t &s = *space;
@@ -297,9 +334,21 @@ extern "C" int skb_local_hex_sumfact(const skb_space_t *space, int form, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   DeviceFlag flag(st);
   SKB_CUDA_TRY(flag.init());
-  const int rc = form == SKB_FORM_LAPLACE
-                     ? launch_hex_sf<SKB_FORM_LAPLACE>(s, tb, out_local, flag.p, st)
-                     : launch_hex_sf<SKB_FORM_MASS>(s, tb, out_local, flag.p, st);
+  // two CTAs of 2 elements per SM: 5.49 ms per C4 step against 5.85 ms for one CTA of 4 (the
+  // barriers of one CTA are covered by the other); debug bits 4, 5 select the other shapes
+  // that were measured (elements, threads, CTAs per SM) - profiles/r2_hex_sumfact.md
+  const int var = (debug_flags() >> 4) & 3;
+  int rc;
+  if (form == SKB_FORM_MASS)
+    rc = launch_hex_sf<SKB_FORM_MASS, 4, 256, 1>(s, tb, em, out_local, flag.p, st);
+  else if (var == 1)
+    rc = launch_hex_sf<SKB_FORM_LAPLACE, 4, 256, 1>(s, tb, em, out_local, flag.p, st);
+  else if (var == 2)
+    rc = launch_hex_sf<SKB_FORM_LAPLACE, 1, 96, 5>(s, tb, em, out_local, flag.p, st);
+  else if (var == 3)
+    rc = launch_hex_sf<SKB_FORM_LAPLACE, 1, 96, 4>(s, tb, em, out_local, flag.p, st);
+  else
+    rc = launch_hex_sf<SKB_FORM_LAPLACE, 2, 128, 2>(s, tb, em, out_local, flag.p, st);
   if (rc != SKB_OK) return rc;
   int herr = 0;
   SKB_CUDA_TRY(flag.read(&herr));

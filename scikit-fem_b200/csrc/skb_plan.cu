@@ -107,6 +107,28 @@ __global__ void csr_reduce_kernel(const double *__restrict__ local, const uint32
   }
 }
 
+// the same sums over element-major local data (nel, Nbv, Nbu): COO entry k = (j Nbv + i) nel + e
+// lives at e Nbu Nbv + i Nbu + j, so the entries one CSR row takes from one element are
+// consecutive in memory instead of nel doubles apart
+__global__ void csr_reduce_em_kernel(const double *__restrict__ local, const uint32_t nel,
+                                     const uint32_t nbu, const uint32_t nbv,
+                                     const uint32_t *__restrict__ perm,
+                                     const uint32_t *__restrict__ segptr, int64_t nnz,
+                                     double *__restrict__ data) {
+  const uint32_t nb2 = nbu * nbv;
+  auto at = [&](uint32_t k) {
+    const uint32_t ji = k / nel, e = k - ji * nel, j = ji / nbv, i = ji - j * nbv;
+    return __ldg(local + (size_t)e * nb2 + i * nbu + j);
+  };
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nnz;
+       s += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t a = segptr[s], b = segptr[s + 1];
+    double acc = at(perm[a]);
+    for (uint32_t k = a + 1; k < b; ++k) acc = acc + at(perm[k]);
+    data[s] = acc;
+  }
+}
+
 __global__ void vec_reduce_kernel(const double *__restrict__ local, const uint32_t *__restrict__ perm,
                                   const uint32_t *__restrict__ segptr,
                                   const int32_t *__restrict__ indptr, int64_t nrows,
@@ -220,6 +242,19 @@ extern "C" int skb_csr_reduce(const double *local, const uint32_t *perm, const u
   if (nnz == 0) return SKB_OK;
   csr_reduce_kernel<<<nblocks(nnz, 256), 256, 0, (cudaStream_t)stream>>>(local, perm, segptr, nnz,
                                                                          data);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+extern "C" int skb_csr_reduce_em(const double *local_em, int64_t nel, int32_t nbu, int32_t nbv,
+                                 const uint32_t *perm, const uint32_t *segptr, int64_t nnz,
+                                 double *data, void *stream) {
+  using namespace skb;
+  if (nnz < 0 || nel <= 0 || nbu <= 0 || nbv <= 0 || (int64_t)nbu * nbv * nel >= (1ll << 32))
+    return SKB_EINVAL;
+  if (nnz == 0) return SKB_OK;
+  csr_reduce_em_kernel<<<nblocks(nnz, 256), 256, 0, (cudaStream_t)stream>>>(
+      local_em, (uint32_t)nel, (uint32_t)nbu, (uint32_t)nbv, perm, segptr, nnz, data);
   count_launch();
   return (int)cudaGetLastError();
 }

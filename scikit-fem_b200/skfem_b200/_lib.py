@@ -40,7 +40,7 @@ SIGNATURES = {
     "skb_local_bilinear": (_INT, [_SP, _INT, _PD, _P, _P]),
     "skb_local_linear": (_INT, [_SP, _INT, _PD, _P, _P]),
     "skb_local_hex_sumfact": (_INT, [_SP, _INT, _I32, C.POINTER(C.c_int32), _PD, _PD,
-                                     C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _P, _P]),
+                                     C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _I32, _P, _P]),
     "skb_plan_scratch_bytes": (_I64, [_I64]),
     "skb_plan_symbolic": (_INT, [_P, _P, _I32, _I32, _I64, _I64, _I64, _P, _INT,
                                  _P, _P, _P, _P, _P, _P, _I64, C.POINTER(_I64), _P]),
@@ -56,6 +56,7 @@ SIGNATURES = {
     "skb_entity_masks": (_INT, [_P, _I32, _I32, _I64, _P, _P, _P, _P]),
     "skb_plan_slot_of_entry": (_INT, [_P, _P, _I64, _P, _P]),
     "skb_csr_reduce": (_INT, [_P, _P, _P, _I64, _P, _P]),
+    "skb_csr_reduce_em": (_INT, [_P, _I64, _I32, _I32, _P, _P, _I64, _P, _P]),
     "skb_vec_reduce": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "skb_tabulate": (_INT, [_SP, _INT, _P, _P, _P, _P, _P]),
     "skb_mapping": (_INT, [_SP, _P, _P, _P, _P]),

@@ -64,6 +64,8 @@ def _torch():
 #                     change, not yet timed on a B200, hence opt-in)
 #   hex_sumfact      ElementHex2 laplace / mass at the default rule by sum factorisation
 #                     (csrc/skb_hex_sf.cu); False: the Gram-matrix tensor-core kernel
+#   element_major    warm generic path: kernels that can (Hex2 sum factorisation) write the
+#                     local data element-major and skb_csr_reduce_em gathers whole sectors
 #   fused_version    2: super-tile / pool kernel (csrc/skb_p1_fused2.cu, fused2.py; options
 #                     fused2_tile, fused2_ring, fused2_pool, fused2_ctas, fused2_S);
 #                     1: the first-generation warp-specialised kernel (options above)
@@ -72,7 +74,7 @@ _CONFIG = {"fused": True, "fused_tile": 512, "fused_threads": 480, "fused_ring":
            "fused_l2_persist": True, "fused_tiling": "morton",
            "fused_version": 2, "fused2_tile": 256, "fused2_ring": 3, "fused2_pool": 2048,
            "fused2_ctas": 0, "fused2_S": None, "fused2_ept": 1, "plan_method": "rows",
-           "hex_sumfact": True}
+           "hex_sumfact": True, "element_major": True}
 
 
 def set_options(**kw):
@@ -509,6 +511,25 @@ class BilinearForm(Form):
             return ubasis.ncomp == 1
         return ubasis.ncomp > 1
 
+    def _local_element_major(self, ubasis):
+        """Element-local data as (nel, Nbv, Nbu) for the warm generic path, or None when no
+        kernel of this form writes that layout (today: ElementHex2 by sum factorisation).
+        ``skb_csr_reduce_em`` then gathers whole sectors instead of one value per sector."""
+        if not (_CONFIG["hex_sumfact"] and _CONFIG["element_major"]
+                and self._native_applicable(ubasis, None, {})
+                and self.native[1] in (_lib.FORM_LAPLACE, _lib.FORM_MASS)):
+            return None
+        tab = _hex_sumfact.tables(ubasis)
+        if tab is None or ubasis.Nbfun ** 2 * ubasis.nelems >= 2 ** 32:
+            return None
+        d = ubasis._dev()
+        out = _torch().empty((ubasis.nelems, ubasis.Nbfun, ubasis.Nbfun),
+                             dtype=_torch().float64, device=d["device"])
+        code = _hex_sumfact.launch(_lib.lib(), d["space"], self.native[1], tab, out.data_ptr(),
+                                   _stream(), element_major=True)
+        _lib.check(code, "skb_local_hex_sumfact")
+        return out
+
     def _local(self, ubasis, vbasis=None, **kwargs):
         """Element-local data (Nbu, Nbv, nel) as a device tensor."""
         torch = _torch()
@@ -627,6 +648,19 @@ class BilinearForm(Form):
                         fused.run(fp, data, _stream(), fast=_CONFIG["fused_arith"] == "fast",
                                   l2_persist=bool(_CONFIG["fused_l2_persist"]))
                     return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
+        if plan is not None and vbasis is None and not kwargs and slot_map is None:
+            # warm call of a form whose kernel can write element-major local data
+            with _lib.nvtx("skfem_b200:local"):
+                local = self._local_element_major(ubasis)
+            if local is not None:
+                data = out if out is not None else torch.empty(
+                    plan.nnz, dtype=torch.float64, device=local.device)
+                code = _lib.lib().skb_csr_reduce_em(
+                    local.data_ptr(), ubasis.nelems, ubasis.Nbfun, ubasis.Nbfun,
+                    plan.perm.data_ptr(), plan.segptr.data_ptr(), plan.nnz, data.data_ptr(),
+                    _stream())
+                _lib.check(code, "skb_csr_reduce_em")
+                return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
         with _lib.nvtx("skfem_b200:local"):
             local = self._local(ubasis, vbasis, **kwargs)
         nz = None

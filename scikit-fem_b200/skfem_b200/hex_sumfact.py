@@ -90,10 +90,11 @@ def tables(basis):
     return out
 
 
-def launch(lib, space, form_id, tab, out_ptr, stream):
+def launch(lib, space, form_id, tab, out_ptr, stream, element_major=False):
     """Call the C entry; returns its status code."""
     as_p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
     return lib.skb_local_hex_sumfact(
         C.byref(space), int(form_id), int(tab["nq"]), as_p(tab["qstride"], C.c_int32),
         as_p(tab["pp"], C.c_double), as_p(tab["g"], C.c_double),
-        as_p(tab["bnode"], C.c_uint8), as_p(tab["vtx"], C.c_uint8), out_ptr, stream)
+        as_p(tab["bnode"], C.c_uint8), as_p(tab["vtx"], C.c_uint8), int(bool(element_major)),
+        out_ptr, stream)

@@ -87,7 +87,7 @@ def test_hex2_value_parity(name, sumfact):
 def test_hex2_sumfact_ragged_batches_subsets_and_zero_jacobian():
     """27 elements (the kernel takes 4 per CTA pass: the last pass is ragged), an element
     subset, and a collapsed element: the sum-factorised kernel against the Gram kernel."""
-    from skfem_b200 import form as F
+    from skfem_b200 import _lib, form as F
     from skfem_b200.models.poisson import laplace, mass
     x = np.linspace(0, 1, 4) ** 1.3
     m = fem.MeshHex.init_tensor(x, np.linspace(0, 2, 4), x)
@@ -96,20 +96,43 @@ def test_hex2_sumfact_ragged_batches_subsets_and_zero_jacobian():
     m = fem.MeshHex(p, m.t)
     for elements in (None, np.array([0, 5, 6, 13, 20, 26])):
         out = {}
-        for sf in (True, False):
-            F.set_options(hex_sumfact=sf)
+        shapes = {"1 x 4": 16, "5 x 1": 32, "4 x 1": 48}    # CTAs per SM x elements per CTA
+        for sf in (True, False) + tuple(shapes):
+            F.set_options(hex_sumfact=bool(sf))
+            _lib.lib().skb_debug_flags(shapes.get(sf, 0))
             try:
                 b = fem.Basis(m, fem.ElementHex2(), elements=elements)
                 out[sf] = [laplace.elemental(b).data, mass.elemental(b).data,
                            laplace.assemble(b), mass.assemble(b)]
             finally:
                 F.set_options(hex_sumfact=True)
+                _lib.lib().skb_debug_flags(0)
+        for k in shapes:                                  # same arithmetic in every CTA shape
+            assert np.array_equal(out[True][0], out[k][0]), k
         for a, c in zip(out[True][:2], out[False][:2]):
             np.testing.assert_allclose(a, c, rtol=RTOL, atol=RTOL * np.abs(c).max())
             assert not np.array_equal(a, c)               # really two different kernels
         for A, B in zip(out[True][2:], out[False][2:]):
             assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
             np.testing.assert_allclose(A.data, B.data, rtol=RTOL, atol=RTOL * np.abs(B.data).max())
+    # warm calls write the local data element-major and reduce it with skb_csr_reduce_em:
+    # same sums in the same order, so the values are the cold call's bit for bit
+    for elements in (None, np.array([0, 5, 6, 13, 20, 26])):
+        b = fem.Basis(m, fem.ElementHex2(), elements=elements)
+        for f in (laplace, mass):
+            cold = f.assemble(b)
+            _lib.lib().skb_launch_count(1)
+            warm = f.assemble(b)
+            assert _lib.lib().skb_launch_count(0) == 2          # local kernel + reduce
+            F.set_options(element_major=False)
+            try:
+                warm_ref = f.assemble(b)
+            finally:
+                F.set_options(element_major=True)
+            for W in (warm, warm_ref):
+                assert np.array_equal(W.indptr, cold.indptr)
+                assert np.array_equal(W.indices, cold.indices)
+                assert np.array_equal(W.data, cold.data)
     # mapping_isoparametric.py:195-196: a cell squeezed to zero volume raises
     p2 = p.copy()
     p2[2, m.t[:, 3]] = p2[2, m.t[0, 3]]
