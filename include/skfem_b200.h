@@ -81,6 +81,13 @@ typedef struct skb_space {
  * flatten (bilinear_form.py:121); Nbu = Nbv = nbs*ncomp.                   */
 int skb_local_bilinear(const skb_space_t *space, int form, const double *params_host,
                        double *out_local, void *stream);
+/* The same element-local data, bit for bit, written element-major: out_local_em is
+ * (nel, Nbv, Nbu), i.e. out_local_em[e][i][j] == out_local[j][i][e] - the layout
+ * skb_csr_reduce_em gathers from on warm re-assembly (the entries a CSR row takes from one
+ * element are then consecutive in memory).  Affine meshes at the default rules of P1 / P2
+ * (compile-time rule sizes); SKB_EINVAL otherwise - callers then use skb_local_bilinear.   */
+int skb_local_bilinear_em(const skb_space_t *space, int form, const double *params_host,
+                          double *out_local_em, void *stream);
 /* out_local: (Nbv, nel) float64 (linear_form.py:41-44).                    */
 int skb_local_linear(const skb_space_t *space, int form, const double *params_host,
                      double *out_local, void *stream);

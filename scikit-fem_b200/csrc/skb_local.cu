@@ -240,7 +240,11 @@ __device__ __forceinline__ double elasticity_sparse(int nu, int nv, const double
 
 // NQP > 0: the rule size is a compile-time constant - the gradient / dx arrays and the NQP
 // terms of an entry then live in registers and numpy's pairwise sum unrolls (pw_sum_fixed).
-template <int DIM, bool VEC, int NQP = 0>
+// EM: element-major output (nel, Nbv, Nbu) for skb_csr_reduce_em.  The roles of the two loops
+// are swapped (test function outside, trial function inside) so that a thread writes the row
+// of its element it is working on left to right; every entry is still its own pairwise sum of
+// the same terms, i.e. the same bits.
+template <int DIM, bool VEC, int NQP = 0, bool EM = false>
 __global__ void __launch_bounds__(128)
 local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double two_mu,
                            double *__restrict__ out) {
@@ -257,26 +261,29 @@ local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double 
     affine_load<DIM>(g, s.p, s.npts, s.t, s.nel_total, eg);
     affine_invert(g);
     const double absdet = fabs(g.det);
-    double gu[MAXQ][DIM], gv[MAXQ][DIM], dxq[MAXQ];
+    double go[MAXQ][DIM], gi[MAXQ][DIM], dxq[MAXQ];
 #pragma unroll
     for (int q = 0; q < MAXQ; ++q)
       if (q < nqp) dxq[q] = absdet * tab.W[q];                      // cell_basis.py:104-105
-    for (int jb = 0; jb < nbs; ++jb) {
+    for (int ob = 0; ob < nbs; ++ob) {                // outer function: trial (test when EM)
 #pragma unroll
       for (int q = 0; q < MAXQ; ++q)
-        if (q < nqp) push_grad<DIM>(g.inv, tab.dphi + jb * DIM * nqp, nqp, q, gu[q]);
-      const double *pj = tab.phi + jb * nqp;
-      for (int ib = 0; ib < nbs; ++ib) {
+        if (q < nqp) push_grad<DIM>(g.inv, tab.dphi + ob * DIM * nqp, nqp, q, go[q]);
+      for (int nb_ = 0; nb_ < nbs; ++nb_) {           // inner function: test (trial when EM)
 #pragma unroll
         for (int q = 0; q < MAXQ; ++q)
-          if (q < nqp) push_grad<DIM>(g.inv, tab.dphi + ib * DIM * nqp, nqp, q, gv[q]);
-        const double *pi = tab.phi + ib * nqp;
+          if (q < nqp) push_grad<DIM>(g.inv, tab.dphi + nb_ * DIM * nqp, nqp, q, gi[q]);
+        const int jb = EM ? nb_ : ob, ib = EM ? ob : nb_;
+        const double(*gu)[DIM] = EM ? gi : go;
+        const double(*gv)[DIM] = EM ? go : gi;
+        const double *pj = tab.phi + jb * nqp, *pi = tab.phi + ib * nqp;
         // nu, nv become compile-time constants after unrolling, which lets the
         // compiler keep only the structurally non-zero terms of the integrand
 #pragma unroll
-        for (int nu = 0; nu < NC; ++nu)
+        for (int n0 = 0; n0 < NC; ++n0)
 #pragma unroll
-          for (int nv = 0; nv < NC; ++nv) {
+          for (int n1 = 0; n1 < NC; ++n1) {
+            const int nu = EM ? n1 : n0, nv = EM ? n0 : n1;
             auto f = [&](int q) -> double {
               double val;
               if (!VEC) {
@@ -310,7 +317,8 @@ local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double 
             } else {
               r = pw_sum(nqp, f);
             }
-            out[((int64_t)J * nb + I) * s.nel + e] = r;
+            if (EM) out[((int64_t)e * nb + I) * nb + J] = r;
+            else out[((int64_t)J * nb + I) * s.nel + e] = r;
           }
       }
     }
@@ -330,7 +338,7 @@ local_affine_cached_kernel(const skb_space_t s, int form, double lambda, double 
 //    per pair.  P2 tetrahedra: 14.4 k instead of 40.7 k FP64 operations.
 // numpy's pairwise sum is replicated with compile-time loops (pw_sum_fixed).
 // ---------------------------------------------------------------------------
-template <int DIM, int NQP>
+template <int DIM, int NQP, bool EM = false>
 __global__ void __launch_bounds__(128)
 local_affine_sym_kernel(const skb_space_t s, int form, double *__restrict__ out) {
   extern __shared__ double smem[];
@@ -373,8 +381,13 @@ local_affine_sym_kernel(const skb_space_t s, int form, double *__restrict__ out)
           term[q] = val * dxq[q];                                   // bilinear_form.py:151
         }
         const double v = pw_sum_fixed<NQP>(term);
-        out[((int64_t)jb * nbs + ib) * s.nel + e] = v;
-        if (jb != ib) out[((int64_t)ib * nbs + jb) * s.nel + e] = v;
+        if (EM) {                                   // (nel, Nbv, Nbu), see the cached kernel
+          out[((int64_t)e * nbs + ib) * nbs + jb] = v;
+          if (jb != ib) out[((int64_t)e * nbs + jb) * nbs + ib] = v;
+        } else {
+          out[((int64_t)jb * nbs + ib) * s.nel + e] = v;
+          if (jb != ib) out[((int64_t)ib * nbs + jb) * s.nel + e] = v;
+        }
       }
     }
   }
@@ -472,7 +485,7 @@ static int grid_for(int64_t work_items, int block, int per_sm) {
   return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
-template <bool BILINEAR>
+template <bool BILINEAR, bool EM = false>
 static int launch_local(const skb_space_t *sp, int form, const double *params, double *out,
                         cudaStream_t st) {
   if (!sp || sp->nel < 0) return SKB_EINVAL;
@@ -518,7 +531,7 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
     if (BILINEAR && !vec && !(debug_flags() & 8)) {
 #define SKB_LAUNCH_SYM(D, Q)                                                                 \
   if (s.dim == D && s.nqp == Q) {                                                            \
-    auto k = local_affine_sym_kernel<D, Q>;                                                  \
+    auto k = local_affine_sym_kernel<D, Q, EM>;                                                \
     if (smem > 48 * 1024)                                                                    \
       SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                         (int)smem));                                         \
@@ -538,7 +551,7 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
     if (BILINEAR && vec && !(debug_flags() & 8)) {
 #define SKB_LAUNCH_CACHED_FIXED(D, Q)                                                        \
   if (s.dim == D && s.nqp == Q) {                                                            \
-    auto k = local_affine_cached_kernel<D, true, Q>;                                         \
+    auto k = local_affine_cached_kernel<D, true, Q, EM>;                                       \
     if (smem > 48 * 1024)                                                                    \
       SKB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                         (int)smem));                                         \
@@ -552,6 +565,7 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
       SKB_LAUNCH_CACHED_FIXED(2, 3)
 #undef SKB_LAUNCH_CACHED_FIXED
     }
+    if (EM) return SKB_EINVAL;       // element-major output: the fixed-rule kernels above only
     if (BILINEAR && vec && s.nqp <= LOCAL_MAXQ && !(debug_flags() & 8)) {
       if (s.dim == 2 && !vec) SKB_LAUNCH_CACHED(2, false);
       else if (s.dim == 2 && vec) SKB_LAUNCH_CACHED(2, true);
@@ -570,6 +584,7 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
     return (int)cudaGetLastError();
   }
   if (s.mapping == SKB_MAP_ISO_HEX1) {
+    if (EM) return SKB_EINVAL;
     if (s.dim != 3 || s.nnodes != 8 || vec || !s.mdphi) return SKB_EINVAL;
     size_t smem = sizeof(double) * 10 * (size_t)s.nqp;
     if (smem > 200 * 1024) return SKB_ETOOBIG;
@@ -604,6 +619,13 @@ static int launch_local(const skb_space_t *sp, int form, const double *params, d
 extern "C" int skb_local_bilinear(const skb_space_t *space, int form, const double *params_host,
                                   double *out_local, void *stream) {
   return skb::launch_local<true>(space, form, params_host, out_local, (cudaStream_t)stream);
+}
+
+extern "C" int skb_local_bilinear_em(const skb_space_t *space, int form,
+                                     const double *params_host, double *out_local_em,
+                                     void *stream) {
+  return skb::launch_local<true, true>(space, form, params_host, out_local_em,
+                                       (cudaStream_t)stream);
 }
 
 extern "C" int skb_local_linear(const skb_space_t *space, int form, const double *params_host,

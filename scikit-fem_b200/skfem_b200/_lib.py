@@ -16,6 +16,7 @@ SKB_MAP_AFFINE, SKB_MAP_ISO_HEX1 = 0, 1
 FORM_LAPLACE, FORM_MASS, FORM_VECTOR_LAPLACE, FORM_ELASTICITY = 0, 1, 2, 3
 LFORM_UNIT_LOAD = 0
 
+SKB_EINVAL = -1
 SKB_ETOOBIG = -2
 ERRORS = {-1: "SKB_EINVAL: bad argument / unsupported combination",
           -2: "SKB_ETOOBIG: tables do not fit on-chip or index overflow",
@@ -38,6 +39,7 @@ _PD = C.POINTER(C.c_double)
 
 SIGNATURES = {
     "skb_local_bilinear": (_INT, [_SP, _INT, _PD, _P, _P]),
+    "skb_local_bilinear_em": (_INT, [_SP, _INT, _PD, _P, _P]),
     "skb_local_linear": (_INT, [_SP, _INT, _PD, _P, _P]),
     "skb_local_hex_sumfact": (_INT, [_SP, _INT, _I32, C.POINTER(C.c_int32), _PD, _PD,
                                      C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _I32, _P, _P]),

@@ -513,21 +513,33 @@ class BilinearForm(Form):
 
     def _local_element_major(self, ubasis):
         """Element-local data as (nel, Nbv, Nbu) for the warm generic path, or None when no
-        kernel of this form writes that layout (today: ElementHex2 by sum factorisation).
-        ``skb_csr_reduce_em`` then gathers whole sectors instead of one value per sector."""
-        if not (_CONFIG["hex_sumfact"] and _CONFIG["element_major"]
-                and self._native_applicable(ubasis, None, {})
-                and self.native[1] in (_lib.FORM_LAPLACE, _lib.FORM_MASS)):
+        kernel of this form writes that layout (ElementHex2 by sum factorisation; P1 / P2
+        library forms on affine meshes at their default rules).  ``skb_csr_reduce_em`` then
+        gathers whole sectors instead of one value per sector."""
+        if not (_CONFIG["element_major"] and self._native_applicable(ubasis, None, {})):
             return None
-        tab = _hex_sumfact.tables(ubasis)
-        if tab is None or ubasis.Nbfun ** 2 * ubasis.nelems >= 2 ** 32:
+        nb = ubasis.Nbfun
+        if nb * nb * ubasis.nelems >= 2 ** 32 or self.native[1] in ubasis.__dict__.get(
+                "_no_em", ()):
             return None
+        torch = _torch()
         d = ubasis._dev()
-        out = _torch().empty((ubasis.nelems, ubasis.Nbfun, ubasis.Nbfun),
-                             dtype=_torch().float64, device=d["device"])
-        code = _hex_sumfact.launch(_lib.lib(), d["space"], self.native[1], tab, out.data_ptr(),
-                                   _stream(), element_major=True)
-        _lib.check(code, "skb_local_hex_sumfact")
+        _, kid, params, _ = self.native
+        out = torch.empty((ubasis.nelems, nb, nb), dtype=torch.float64, device=d["device"])
+        tab = _hex_sumfact.tables(ubasis) if _CONFIG["hex_sumfact"] and kid in (
+            _lib.FORM_LAPLACE, _lib.FORM_MASS) else None
+        if tab is not None:
+            code = _hex_sumfact.launch(_lib.lib(), d["space"], kid, tab, out.data_ptr(),
+                                       _stream(), element_major=True)
+            _lib.check(code, "skb_local_hex_sumfact")
+            return out
+        cparams = None if params is None else (C.c_double * len(params))(*params)
+        code = _lib.lib().skb_local_bilinear_em(C.byref(d["space"]), kid, cparams,
+                                                out.data_ptr(), _stream())
+        if code == _lib.SKB_EINVAL:               # no element-major kernel for this space
+            ubasis.__dict__.setdefault("_no_em", set()).add(kid)
+            return None
+        _lib.check(code, "skb_local_bilinear_em")
         return out
 
     def _local(self, ubasis, vbasis=None, **kwargs):

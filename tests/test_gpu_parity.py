@@ -141,6 +141,52 @@ def test_hex2_sumfact_ragged_batches_subsets_and_zero_jacobian():
         laplace.elemental(b)
 
 
+@pytest.mark.parametrize("name,refdom,elem,vector", [
+    ("tet_p1_morphed5", "tet", fem.ElementTetP1, False),
+    ("tet_p2_tensor3", "tet", fem.ElementTetP2, False),
+    ("tri_p2_morphed3", "tri", fem.ElementTriP2, False),
+    ("tet_vp2_elasticity2", "tet", fem.ElementTetP2, True),
+    ("tet_p1_ball2", "tet", fem.ElementTetP1, True),
+])
+def test_element_major_warm_calls_are_bit_identical(name, refdom, elem, vector):
+    """Warm calls of library forms on affine meshes write the element-local data element-major
+    (skb_local_bilinear_em) and reduce it with skb_csr_reduce_em: the same entries, summed in
+    the same order - CSR values equal to the cold call's (reference layout) bit for bit, with
+    and without an element subset."""
+    from skfem_b200 import _lib, form as F
+    from skfem_b200.models.elasticity import linear_elasticity
+    from skfem_b200.models.poisson import laplace, mass, vector_laplace
+    from cases import LAME
+    g = load(name)
+    m = mesh_from(g, refdom)
+    e = fem.ElementVector(elem()) if vector else elem()
+    fs = [linear_elasticity(*LAME), vector_laplace] if vector else [laplace, mass]
+    F.set_options(fused=False)                    # P1 tets: keep the generic path
+    try:
+        for elements in (None, np.arange(1, m.nelements, 3)):
+            b = fem.Basis(m, e, elements=elements)
+            for f in fs:
+                cold = f.assemble(b)
+                _lib.lib().skb_launch_count(1)
+                warm = f.assemble(b)
+                assert _lib.lib().skb_launch_count(0) == 2      # local kernel + reduce
+                em = f._local_element_major(b)
+                assert em is not None and tuple(em.shape) == (b.nelems, b.Nbfun, b.Nbfun)
+                ref = f._local(b)                                # (Nbu, Nbv, nel)
+                assert bool((em == ref.permute(2, 1, 0)).all())
+                F.set_options(element_major=False)
+                try:
+                    plain = f.assemble(b)
+                finally:
+                    F.set_options(element_major=True)
+                for W in (warm, plain):
+                    assert np.array_equal(W.indptr, cold.indptr)
+                    assert np.array_equal(W.indices, cold.indices)
+                    assert np.array_equal(W.data, cold.data)
+    finally:
+        F.set_options(fused=True)
+
+
 def test_known_answers():
     # doctest of skfem/assembly/__init__.py:38-46
     from skfem_b200.models.poisson import mass, unit_load, laplace
