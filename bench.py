@@ -591,8 +591,8 @@ CONFIGS = {
     "p2": ("ElementTetP2 laplace on MeshTet.init_tensor {n}^3 pts (the metric's P2 case)", 61),
     "c3": ("ElementVector(ElementTetP2) linear_elasticity(lame_parameters(1e3, 0.3)) on "
            "MeshTet.init_tensor {n}^3 pts (BASELINE configs[2])", 70),
-    "c4": ("ElementHex2 laplace on MeshHex.init_tensor {n}^3 pts (BASELINE configs[3], FP64 "
-           "tensor-core Gram kernel)", 65),
+    "c4": ("ElementHex2 laplace on MeshHex.init_tensor {n}^3 pts (BASELINE configs[3], "
+           "sum-factorised local kernel)", 65),
 }
 
 

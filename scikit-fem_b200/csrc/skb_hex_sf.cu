@@ -20,12 +20,20 @@
 // against the reference on the CPU in tests/test_hex2_sumfact_cpu.py), so the
 // quadrature sum may be re-associated; ElementHex1 (bit-exact) keeps the scalar kernel.
 //
-// Mapping onto the SM: E elements per CTA, one CTA per SM (177 kB of shared memory).
-// Every stage is a flat list of work items (element, row) spread over the CTA; an item
-// loads its 7 inputs of one combo from shared memory once and runs 9 x 7 FMAs whose
-// second operand is a *kernel parameter at a compile-time offset* - the 1-D tables
-// live in the constant bank and feed the DFMAs directly, no load instructions.  All
-// loops over combos, groups and table rows are unrolled.
+// Mapping onto the SM: E elements per CTA pass (2, two CTAs per SM, 88 kB of shared memory
+// each).  Every stage is a flat list of work items (element, row) spread over the CTA; an item
+// loads its 7 inputs of one combo from shared memory once and runs 9 x 7 FMAs whose second
+// operand is a *kernel parameter at a compile-time offset* - the 1-D tables live in the
+// constant bank (LDCU into uniform registers, DFMA R, R, UR, R), no shared-memory traffic for
+// them.  All loops over combos, groups and table rows are unrolled.  Geometry: the 12 edge
+// differences of the trilinear map are fetched one pass ahead (vertex numbers and coordinates
+// at two different points of the pass, so neither latency is exposed); Jacobian column f
+// depends on the two other axes only (3 x 49 values per element), G needs 343 points.
+// The last stage adds the symmetric and the two off-diagonal parts and writes either the
+// reference layout (27, 27, nel) or, for warm re-assembly, element-major (nel, 27, 27) -
+// 729 consecutive doubles per element, which skb_csr_reduce_em gathers sector by sector.
+// Measured (BASELINE configs[3], 262 144 elements, one B200): 4.1 ms against 18.2 ms for the
+// Gram kernel; ncu stage split and the CTA shapes tried: profiles/r2_hex_sumfact.md.
 #include "skb_common.cuh"
 
 namespace skb {
