@@ -29,14 +29,21 @@ xs = np.linspace(0, 1, max((n + 1) // 2, 25))   # >= 65 536 tets: entities / DOF
 ms = fem.MeshTet.init_tensor(xs, xs, xs)
 b2 = fem.Basis(ms, fem.ElementTetP2())
 laplace.assemble_device(b2)
+laplace.assemble_device(b2)                # warm: element-major sym kernel + csr_reduce_em
 bv = fem.Basis(ms, fem.ElementVector(fem.ElementTetP2()))
-linear_elasticity(*lame_parameters(1e3, 0.3)).assemble_device(bv)   # cached vector kernel
+el = linear_elasticity(*lame_parameters(1e3, 0.3))
+el.assemble_device(bv)                     # cached vector kernel
+el.assemble_device(bv)                     # warm: its element-major variant
 xh = np.linspace(0, 1, max((n + 1) // 2, 42))   # >= 65 536 hexes
 mh = fem.MeshHex.init_tensor(xh, xh, xh)
 laplace.assemble_device(fem.Basis(mh, fem.ElementHex1()))           # local_hex
 bh2 = fem.Basis(mh, fem.ElementHex2())
-laplace.assemble_device(bh2)                                         # DMMA Gram kernel
+laplace.assemble_device(bh2)                                         # sum-factorised kernel
+laplace.assemble_device(bh2)                                         # warm: element-major output
 mass.assemble_device(bh2)
+F.set_options(hex_sumfact=False)
+laplace.assemble_device(fem.Basis(mh, fem.ElementHex2()))            # DMMA Gram kernel
+F.set_options(hex_sumfact=True)
 # traced form with a coefficient field: tabulate + qp_reduce
 k = b1.interpolate(np.ones(b1.N))
 fem.BilinearForm(lambda u, v, w: w["k"] * dot(grad(u), grad(v))).assemble_device(b1, k=k)
