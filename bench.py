@@ -673,6 +673,43 @@ def run_config(args):
             (4 * nbs * nel if basis.element_dofs is not m.t else 0))
     peak, peak_src = peaks()
     achieved = algo / (ms_step * 1e-3) / 1e9
+    # end to end before the CPU arm: with the reference (multi-GB numpy temporaries for Hex2)
+    # run first, 3 of 4 C4 runs showed 0.2 - 0.4 s stalls per cold call, all inside the plan
+    # builder's stream synchronisations (cProfile, profiles/r2_hex_sumfact.md); without the CPU
+    # arm, and in tools/c4_e2e_times.py, the same call takes 52 ms
+    e2e = None
+    if not args.no_e2e and nnz < 2.5e8:
+        p_host, t_host = m.p, m.t
+
+        def e2e_step():
+            mm = type(m)(p_host, t_host)
+            return form.assemble(fem.Basis(mm, elem))
+        # the first calls grow torch's pinned-host pool for the result arrays (seconds for the
+        # 1.6 GB of C4: tools/c4_e2e_times.py), so four untimed calls like the default config
+        for _ in range(4):
+            Ah = e2e_step()
+        torch.cuda.synchronize()
+        k = 3
+        if os.environ.get("BENCH_PROFILE_E2E"):       # host-side profile of one call -> stderr
+            import cProfile, pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            e2e_step()
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumtime").print_stats(25)
+        calls = []
+        t0 = time.perf_counter()
+        for _ in range(k):
+            t1 = time.perf_counter()
+            Ah = e2e_step()
+            calls.append(1e3 * (time.perf_counter() - t1))
+        dt = (time.perf_counter() - t0) / k
+        e2e = {"value": nel / dt, "unit": "elements/s", "ms_calls": calls,
+               "h2d_bytes_per_step": int(m.p.nbytes + m.t.nbytes),
+               "d2h_bytes_per_step": int(Ah.data.nbytes + Ah.indices.nbytes + Ah.indptr.nbytes),
+               "ms_per_step": 1e3 * dt,
+               "what": "cold: Mesh(p,t) + Basis (topology, DOF numbering) + form.assemble -> "
+                       "scipy csr_matrix, plan build included"}
     # CPU: the reference itself on a bounded chunk of the same mesh (CellBasis(elements=...))
     cpu = None
     if not args.no_cpu:
@@ -688,27 +725,6 @@ def run_config(args):
                    "sample": "the unmodified reference (oracle/_ref), single thread, "
                              "Basis(elements=first {} elements) + assemble of the same mesh, "
                              "{:.1f} s".format(len(chunk), dt)}
-    e2e = None
-    if not args.no_e2e and nnz < 2.5e8:
-        p_host, t_host = m.p, m.t
-
-        def e2e_step():
-            mm = type(m)(p_host, t_host)
-            return form.assemble(fem.Basis(mm, elem))
-        for _ in range(2):
-            Ah = e2e_step()
-        torch.cuda.synchronize()
-        k = 3
-        t0 = time.perf_counter()
-        for _ in range(k):
-            Ah = e2e_step()
-        dt = (time.perf_counter() - t0) / k
-        e2e = {"value": nel / dt, "unit": "elements/s",
-               "h2d_bytes_per_step": int(m.p.nbytes + m.t.nbytes),
-               "d2h_bytes_per_step": int(Ah.data.nbytes + Ah.indices.nbytes + Ah.indptr.nbytes),
-               "ms_per_step": 1e3 * dt,
-               "what": "cold: Mesh(p,t) + Basis (topology, DOF numbering) + form.assemble -> "
-                       "scipy csr_matrix, plan build included"}
     line = {
         "metric": "assembly elements/s (FP64, config {})".format(name), "value": nel / (ms_step * 1e-3),
         "unit": "elements/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
