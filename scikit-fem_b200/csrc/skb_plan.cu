@@ -262,9 +262,10 @@ extern "C" int skb_csr_reduce_em(const double *local_em, int64_t nel, int32_t nb
                                  const uint32_t *perm, const uint32_t *segptr, int64_t nnz,
                                  double *data, void *stream) {
   using namespace skb;
-  if (nnz < 0 || nel <= 0 || nbu <= 0 || nbv <= 0 || (int64_t)nbu * nbv * nel >= (1ll << 32))
+  if (nnz < 0 || nel < 0 || nbu <= 0 || nbv <= 0 || (int64_t)nbu * nbv * nel >= (1ll << 32))
     return SKB_EINVAL;
   if (nnz == 0) return SKB_OK;
+  if (nel == 0) return SKB_EINVAL;           // slots without entries cannot exist
   csr_reduce_em_kernel<<<nblocks(nnz, 256), 256, 0, (cudaStream_t)stream>>>(
       local_em, (uint32_t)nel, (uint32_t)nbu, (uint32_t)nbv, perm, segptr, nnz, data);
   count_launch();

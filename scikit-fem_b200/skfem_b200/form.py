@@ -660,7 +660,8 @@ class BilinearForm(Form):
                         fused.run(fp, data, _stream(), fast=_CONFIG["fused_arith"] == "fast",
                                   l2_persist=bool(_CONFIG["fused_l2_persist"]))
                     return DeviceCSR(plan.indptr, plan.indices, data, plan.shape)
-        if plan is not None and vbasis is None and not kwargs and slot_map is None:
+        if (plan is not None and vbasis is None and not kwargs and slot_map is None
+                and ubasis.nelems > 0 and plan.nnz > 0):
             # warm call of a form whose kernel can write element-major local data
             with _lib.nvtx("skfem_b200:local"):
                 local = self._local_element_major(ubasis)

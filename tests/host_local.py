@@ -56,6 +56,20 @@ extern "C" int host_local_affine(const skb_space_t *s, int form, double lambda, 
 #undef FIX
     return -1;
   }
+  if (cached == 5) {     // the same, element-major output (nel, Nbv, Nbu)
+    if (!vec || !bilinear) return -1;
+#define FIX(D, Q) if (s->dim == D && s->nqp == Q) { skb::local_affine_cached_kernel<D, true, Q, true>(*s, form, lambda, two_mu, out); return 0; }
+    FIX(3, 4) FIX(3, 11) FIX(2, 3) FIX(2, 6)
+#undef FIX
+    return -1;
+  }
+  if (cached == 4) {     // symmetric kernel of scalar elements, element-major output
+    if (vec || !bilinear) return -1;
+#define SYM(D, Q) if (s->dim == D && s->nqp == Q) { skb::local_affine_sym_kernel<D, Q, true>(*s, form, out); return 0; }
+    SYM(3, 4) SYM(3, 11) SYM(2, 3) SYM(2, 6)
+#undef SYM
+    return -1;
+  }
   if (cached == 2) {     // register-cached symmetric kernel of scalar elements
     if (vec || !bilinear) return -1;
 #define SYM(D, Q) if (s->dim == D && s->nqp == Q) { skb::local_affine_sym_kernel<D, Q>(*s, form, out); return 0; }

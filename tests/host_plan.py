@@ -45,6 +45,11 @@ extern "C" void host_csr_reduce(const double *local, const uint32_t *perm, const
                                 int64_t nnz, double *data) {
   csr_reduce_kernel(local, perm, segptr, nnz, data);
 }
+extern "C" void host_csr_reduce_em(const double *local_em, uint32_t nel, uint32_t nbu, uint32_t nbv,
+                                   const uint32_t *perm, const uint32_t *segptr, int64_t nnz,
+                                   double *data) {
+  csr_reduce_em_kernel(local_em, nel, nbu, nbv, perm, segptr, nnz, data);
+}
 extern "C" void host_vec_reduce(const double *local, const uint32_t *perm, const uint32_t *segptr,
                                 const int32_t *indptr, int64_t nrows, double *vec) {
   vec_reduce_kernel(local, perm, segptr, indptr, nrows, vec);
@@ -118,6 +123,15 @@ def csr_reduce(local, plan):
     data = np.full(plan["nnz"], np.nan)
     lib.host_csr_reduce(_p(local), _p(plan["perm"]), _p(plan["segptr"]), C.c_int64(plan["nnz"]),
                         _p(data))
+    return data
+
+
+def csr_reduce_em(local_em, nel, nbu, nbv, plan):
+    """skb_csr_reduce_em: the plan's COO indices against element-major local data."""
+    lib = C.CDLL(build())
+    data = np.full(plan["nnz"], np.nan)
+    lib.host_csr_reduce_em(_p(local_em), C.c_uint32(nel), C.c_uint32(nbu), C.c_uint32(nbv),
+                           _p(plan["perm"]), _p(plan["segptr"]), C.c_int64(plan["nnz"]), _p(data))
     return data
 
 

@@ -75,6 +75,48 @@ def test_local_kernels_match_reference_bitwise(name):
     assert checked > 0
 
 
+@pytest.mark.parametrize("name", AFFINE)
+def test_element_major_kernels_and_reduce_on_the_cpu(name):
+    """The element-major variants of the fixed-rule kernels (skb_local_bilinear_em) write the
+    reference's element-local data bit for bit, transposed to (nel, Nbv, Nbu), and
+    ``csr_reduce_em_kernel`` turns them into the same CSR values as ``csr_reduce_kernel`` does
+    from the reference layout - from the shipped sources, on the host."""
+    import host_plan
+    refdom, ename, vector, bil, lin, has_local = CASES[name]
+    g = load(name)
+    basis = fem.Basis(mesh_from(g, refdom), element_from(ename, vector))
+    keep = []
+    sp = _space(basis, keep)
+    lib = host_local.lib()
+    nb, nel, N = basis.Nbfun, basis.nelems, basis.N
+    edofs = np.ascontiguousarray(basis.element_dofs)
+    checked = 0
+    for f in bil:
+        if f not in NATIVE:
+            continue
+        kid, _ = NATIVE[f]
+        lam, two_mu = (LAME[0], 2. * LAME[1]) if f == "elasticity" else (1.0, 2.0)
+        outs = {}
+        for cached in ((3, 5) if vector else (2, 4)):
+            out = np.full(nb * nb * nel, np.nan)
+            rc = lib.host_local_affine(C.byref(sp), C.c_int(kid), C.c_double(lam),
+                                       C.c_double(two_mu), C.c_void_p(out.ctypes.data),
+                                       C.c_int(1), C.c_int(cached))
+            assert rc == 0, (name, f, cached)
+            outs[cached] = out
+        local, em = outs[3 if vector else 2], outs[5 if vector else 4]
+        if has_local:
+            assert np.array_equal(local, g[f + "_local"])
+        # em[e][i][j] == local[j][i][e]
+        assert np.array_equal(em.reshape(nel, nb, nb), local.reshape(nb, nb, nel).transpose(2, 1, 0))
+        plan = host_plan.symbolic(local, edofs, edofs, nel, N, N, drop_zeros=True)
+        data = host_plan.csr_reduce(local, plan)
+        assert np.array_equal(host_plan.csr_reduce_em(em, nel, nb, nb, plan), data), (name, f)
+        _check_csr(plan, data, g, f)
+        checked += 1
+    assert checked > 0
+
+
 def _check_csr(plan, data, g, f):
     assert np.array_equal(plan["indptr"], g[f + "_indptr"]), f
     assert np.array_equal(plan["indices"], g[f + "_indices"]), f
