@@ -7,8 +7,9 @@ inter-thread communication.  Run as a single thread of a single block (``blockDi
 source compiles with g++ - CUDA intrinsics spelled in standard C++ as in tests/host_arith.py,
 ``extern __shared__`` replaced by a static buffer, ``-ffp-contract=off`` for nvcc's
 ``-fmad=false``.  tests/test_local_kernels_cpu.py compares the output bit for bit with the
-reference's element-local data (tests/golden).  The hexahedral kernels (block-cooperative) and
-everything with TMA / tensor cores stay GPU-only.  Not product code.
+reference's element-local data (tests/golden).  The block-cooperative hexahedral kernels run on
+the host through tests/host_block.py (one host thread per CUDA thread); everything with TMA /
+tensor cores stays GPU-only.  Not product code.
 """
 import ctypes as C
 import os
