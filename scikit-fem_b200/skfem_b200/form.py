@@ -519,8 +519,7 @@ class BilinearForm(Form):
         if not (_CONFIG["element_major"] and self._native_applicable(ubasis, None, {})):
             return None
         nb = ubasis.Nbfun
-        if nb * nb * ubasis.nelems >= 2 ** 32 or self.native[1] in ubasis.__dict__.get(
-                "_no_em", ()):
+        if nb * nb * ubasis.nelems >= 2 ** 32 or ubasis._plans.get(("no-em", self.native[1])):
             return None
         torch = _torch()
         d = ubasis._dev()
@@ -537,7 +536,7 @@ class BilinearForm(Form):
         code = _lib.lib().skb_local_bilinear_em(C.byref(d["space"]), kid, cparams,
                                                 out.data_ptr(), _stream())
         if code == _lib.SKB_EINVAL:               # no element-major kernel for this space
-            ubasis.__dict__.setdefault("_no_em", set()).add(kid)
+            ubasis._plans[("no-em", kid)] = True
             return None
         _lib.check(code, "skb_local_bilinear_em")
         return out
