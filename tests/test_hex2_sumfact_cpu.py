@@ -70,7 +70,8 @@ def emulate(basis, tab, form):
     return A                                                 # (nel, 27, 27)
 
 
-@pytest.mark.parametrize("name", ["hex2_tensor2", "hex2_morphed2", "hex2_morphed4"])
+@pytest.mark.parametrize("name", ["hex2_tensor2", "hex2_morphed2", "hex2_morphed4",
+                                  "hex2_boxes3"])
 def test_hex2_sum_factorisation_matches_reference(name):
     g = load(name)
     b = fem.Basis(mesh_from(g, "hex"), fem.ElementHex2())

@@ -65,7 +65,8 @@ def _sumfact(sp, form, tab, nel, em=False, shape=0, grid=3):
 
 @pytest.mark.parametrize("name,elem", [("hex1_tensor3", fem.ElementHex1),
                                        ("hex1_morphed3", fem.ElementHex1),
-                                       ("hex2_morphed4", fem.ElementHex2)])
+                                       ("hex2_morphed4", fem.ElementHex2),
+                                       ("hex2_boxes3", fem.ElementHex2)])
 def test_scalar_hex_kernel_matches_reference_bitwise(name, elem):
     g = load(name)
     basis = fem.Basis(mesh_from(g, "hex"), elem())
@@ -86,7 +87,8 @@ def test_scalar_hex_kernel_matches_reference_bitwise(name, elem):
     assert checked > 0
 
 
-@pytest.mark.parametrize("name", ["hex2_tensor2", "hex2_morphed2", "hex2_morphed4"])
+@pytest.mark.parametrize("name", ["hex2_tensor2", "hex2_morphed2", "hex2_morphed4",
+                                  "hex2_boxes3"])
 def test_sum_factorised_kernel_matches_reference(name):
     g = load(name)
     basis = fem.Basis(mesh_from(g, "hex"), fem.ElementHex2())
