@@ -94,7 +94,9 @@ def enforce(A, b=None, x=None, I=None, D=None, diag=1., overwrite=False):
                                       Aout.data.data_ptr(), D.data_ptr(), D.shape[0],
                                       C.c_double(float(diag)), missing.data_ptr(), _stream())
     _lib.check(code, "skb_csr_enforce")
-    if int(missing.item()):
+    if int(missing.item()) and float(diag) != 0.:
+        # (diag == 0: the row is zero either way; the reference's setdiag would additionally
+        # store explicit zeros on the diagonal, utils.py:385-388)
         raise NotImplementedError("enforce: a row of D has no stored diagonal entry")
     if b is None:
         return Aout
