@@ -290,3 +290,32 @@ def test_product_never_touches_the_oracle_or_the_reference():
                         if pat.search(line):
                             hits.append("{}:{}: {}".format(f, n, line.strip()))
     assert not hits, hits
+
+
+def test_element_major_request_falls_back_when_no_kernel_writes_it(monkeypatch):
+    """``skb_local_bilinear_em`` answers SKB_EINVAL for spaces without an element-major kernel
+    (hexahedra with the scalar kernel, non-default rules): the warm path must then use the
+    reference layout, and ask only once per (basis, form)."""
+    from skfem_b200 import _lib, form as F
+    from skfem_b200.models.poisson import laplace
+    b = fem.Basis(fem.MeshHex(), fem.ElementHex1())
+    calls = []
+
+    class FakeLib:
+        def skb_local_bilinear_em(self, *args):
+            calls.append(args)
+            return _lib.SKB_EINVAL
+
+    monkeypatch.setattr(F._lib, "lib", lambda: FakeLib())
+    monkeypatch.setattr(F, "_stream", lambda: None)
+    monkeypatch.setattr(type(b), "_dev",
+                        lambda self, device=None: {"device": "cpu", "space": _lib.SkbSpace()})
+    assert laplace._local_element_major(b) is None
+    assert laplace._local_element_major(b) is None
+    assert len(calls) == 1
+    F.set_options(element_major=False)
+    try:
+        assert laplace._local_element_major(fem.Basis(fem.MeshHex(), fem.ElementHex1())) is None
+        assert len(calls) == 1
+    finally:
+        F.set_options(element_major=True)
