@@ -10,7 +10,8 @@
 Host side: thin Python; device side: hand-written sm_100a CUDA kernels behind
 the C ABI in include/skfem_b200.h.  There is no CPU fallback.
 """
-from .mesh import Mesh, MeshTri, MeshTet, MeshHex, MeshTri1, MeshTet1, MeshHex1
+from .mesh import (Mesh, MeshTri, MeshTet, MeshHex, MeshTri1, MeshTet1, MeshHex1,
+                   OrientedBoundary)
 from .element import (Element, ElementH1, ElementTriP1, ElementTriP2, ElementTetP1,
                       ElementTetP2, ElementHex1, ElementHex2, ElementVector)
 from .mapping import MappingAffine, MappingIsoparametric
@@ -37,5 +38,5 @@ __all__ = [
     "FacetBasis", "BoundaryFacetBasis", "ExteriorFacetBasis", "InteriorFacetBasis",
     "DiscreteField", "DeviceArray", "asdevice", "Form", "BilinearForm", "LinearForm",
     "Functional", "COOData", "DeviceCSR", "FormExtraParams", "asm", "helpers", "models",
-    "enforce", "condense", "solve", "solver_iter_pcg", "utils",
+    "enforce", "condense", "solve", "solver_iter_pcg", "utils", "OrientedBoundary",
 ]

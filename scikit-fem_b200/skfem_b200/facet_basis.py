@@ -19,6 +19,7 @@ import numpy as np
 from . import _lib
 from .basis import CellBasis, _torch, default_device
 from .dofs import Dofs
+from .mesh import OrientedBoundary
 from .element import _MonomialElement
 from .quadrature import get_quadrature
 
@@ -82,10 +83,20 @@ class FacetBasis(CellBasis):
         if facets is None:
             self.find = np.nonzero(mesh.f2t[1] == -1)[0].astype(np.int32)
         else:
-            self.find = np.asarray(mesh.normalize_facets(facets))
+            self.find = mesh.normalize_facets(facets)
         self._side = side
-        self.tind = mesh.f2t[side, self.find]
-        self.tind_normals = mesh.f2t[0, self.find]
+        self._facets_arg = self.find
+        if isinstance(self.find, OrientedBoundary):
+            # fix the orientation (facet_basis.py:84-87): traces from the oriented side (or,
+            # side=1, from the other one), normals always from the oriented side
+            ori = self.find.ori
+            self.find = np.asarray(self.find)
+            self.tind = mesh.f2t[(-1) ** side * ori - side, self.find]
+            self.tind_normals = mesh.f2t[ori, self.find]
+        else:
+            self.find = np.asarray(self.find)
+            self.tind = mesh.f2t[side, self.find]
+            self.tind_normals = mesh.f2t[0, self.find]
         if len(self.find) == 0:
             logger.warning("Initializing {} with no facets.".format(type(self).__name__))
         elif self.tind.min() < 0:
@@ -101,7 +112,7 @@ class FacetBasis(CellBasis):
     def with_element(self, elem):
         """Same facets, side and quadrature with another element (facet_basis.py:257-270)."""
         return type(self)(self.mesh, elem, mapping=self.mapping, quadrature=(self.X, self.W),
-                          facets=self.find, side=self._side)
+                          facets=self._facets_arg, side=self._side)
 
     @property
     def nbs(self):

@@ -176,6 +176,23 @@ def _build_entities_device(t, indices, nv, sort, keep=None):
     return host(ent, incidence)
 
 
+class OrientedBoundary(np.ndarray):
+    """An array of facet indices with an orientation per facet (skfem/generic_utils.py:16-28):
+    ``ori[k]`` is the side of ``f2t[:, find[k]]`` the traces and outward normals are taken
+    from (FacetBasis, facet_basis.py:84-89)."""
+
+    def __new__(cls, indices, ori):
+        obj = np.asarray(indices).view(cls)
+        obj.ori = np.array(ori, dtype=int)
+        assert len(obj) == len(obj.ori)
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.ori = getattr(obj, 'ori', None)
+
+
 class Mesh:
     elem = None          # geometry element (class)
     affine = False
@@ -399,13 +416,47 @@ class Mesh:
 
     boundaries = None  # optional {name: facet indices}
 
-    def facets_satisfying(self, test, boundaries_only=False):
-        """Facets whose midpoints satisfy ``test`` (mesh.py:426-446)."""
+    def facets_satisfying(self, test, boundaries_only=False, normal=None):
+        """Facets whose midpoints satisfy ``test`` (mesh.py:426-456); with ``normal`` an
+        ``OrientedBoundary``: orientation 1 where ``normal`` points against the outward
+        normal of the facet's first element."""
         midp = self.p[:, self.facets].mean(axis=1)
         facets = np.nonzero(test(midp))[0].astype(np.int32)
         if boundaries_only:
             facets = np.intersect1d(facets, self.boundary_facets())
+        if normal is not None:
+            ori = 1 * (np.dot(np.asarray(normal, dtype=np.float64),
+                              self._outward_normals(facets)) < 0)
+            return OrientedBoundary(facets, ori)
         return facets
+
+    def _outward_normals(self, facets):
+        """(dim, len(facets)) outward normal directions (not normalised) of the facets with
+        respect to their first element ``f2t[0]`` - the direction of
+        ``MappingAffine.normals`` (mapping_affine.py:248-281), from the vertices alone."""
+        if not self.affine:
+            raise NotImplementedError("oriented facet sets: affine meshes only")
+        fv = self.p[:, self.facets[:, facets]]                  # (dim, nodes, nf)
+        if self.dim() == 2:
+            e = fv[:, 1] - fv[:, 0]
+            n = np.array([e[1], -e[0]])
+        else:
+            a, b = fv[:, 1] - fv[:, 0], fv[:, 2] - fv[:, 0]
+            n = np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2],
+                          a[0] * b[1] - a[1] * b[0]])
+        centre = self.p[:, self.t[:, self.f2t[0, facets]]].mean(axis=1)
+        inward = np.sum(n * (centre - fv[:, 0]), axis=0) > 0
+        return np.where(inward, -n, n)
+
+    def facets_around(self, elements, flip=False):
+        """The oriented facets around a set of elements (mesh.py:458-479): traces and outward
+        normals from inside the set, or from outside it with ``flip=True``."""
+        elements = self.normalize_elements(elements)
+        facets, counts = np.unique(self.t2f[:, elements], return_counts=True)
+        facets = facets[counts == 1]
+        member = np.isin(self.f2t[:, facets], elements).T
+        ori = np.nonzero(~member if flip else member)[1].astype(np.int32)
+        return OrientedBoundary(facets, ori)
 
     def with_boundaries(self, boundaries, boundaries_only=True):
         """Copy of the mesh with named boundaries: ``{name: facet indices | test on
