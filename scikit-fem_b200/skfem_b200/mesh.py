@@ -177,20 +177,24 @@ def _build_entities_device(t, indices, nv, sort, keep=None):
 
 
 class OrientedBoundary(np.ndarray):
-    """An array of facet indices with an orientation per facet (skfem/generic_utils.py:16-28):
-    ``ori[k]`` is the side of ``f2t[:, find[k]]`` the traces and outward normals are taken
-    from (FacetBasis, facet_basis.py:84-89)."""
+    """Facet indices plus one orientation flag per facet (the role of
+    skfem/generic_utils.py:16-28): ``ori[k]`` selects the row of ``f2t[:, find[k]]`` - the
+    element - that traces and outward normals are taken from (FacetBasis,
+    facet_basis.py:84-89).  Behaves like the plain index array everywhere else."""
+    ori = None
 
     def __new__(cls, indices, ori):
-        obj = np.asarray(indices).view(cls)
-        obj.ori = np.array(ori, dtype=int)
-        assert len(obj) == len(obj.ori)
-        return obj
+        self = np.asarray(indices).view(cls)
+        flags = np.array(ori, dtype=int).reshape(-1)
+        if flags.shape[0] != self.shape[0]:
+            raise ValueError("OrientedBoundary: one orientation per facet")
+        self.ori = flags
+        return self
 
-    def __array_finalize__(self, obj):
-        if obj is None:
-            return
-        self.ori = getattr(obj, 'ori', None)
+    def __array_finalize__(self, source):
+        # views and copies keep the flags of the array they come from
+        if source is not None and self.ori is None:
+            self.ori = getattr(source, "ori", None)
 
 
 class Mesh:
