@@ -172,44 +172,6 @@ def test_gpu_facet_scalar(name, refdom, ename):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,refdom,ename,normal", [
-    ("facet_oriented_tri", "tri", "tri_p2", [1., 0.2]),
-    ("facet_oriented_tet", "tet", "tet_p1", [1., 0.2, -0.1])])
-def test_gpu_facet_oriented_sets(name, refdom, ename, normal):
-    """FacetBasis on OrientedBoundary sets (Mesh.facets_around, facets_satisfying(normal=));
-    golden vectors by the real reference (tools/gen_golden_oriented.py)."""
-    import skfem_b200 as fem
-    from skfem_b200.helpers import dot, grad
-    g = load(name)
-    m = (fem.MeshTri if refdom == "tri" else fem.MeshTet)(g["p"], g["t"])
-    e = _elem(fem, ename)
-
-    def interior(x):
-        return np.all((x > 0.2) * (x < 0.8), axis=0)
-    inside = m.elements_satisfying(lambda x: interior(x) * (x[0] < 0.55))
-    sets = {"around": m.facets_around(inside), "around_flip": m.facets_around(inside, flip=True),
-            "normal": m.facets_satisfying(lambda x: interior(x) * (x[0] > 0.3) * (x[0] < 0.7),
-                                          normal=np.array(normal))}
-    flow = fem.BilinearForm(lambda u, v, w: dot(grad(u), w.n) * v + u * v)
-    divthm = fem.Functional(lambda w: dot(w.n, w.x))
-    for key, ob in sets.items():
-        assert np.array_equal(np.asarray(ob), g[key + "_find"])
-        assert np.array_equal(ob.ori, g[key + "_ori"])
-        for side in (0, 1):
-            k = "{}_s{}".format(key, side)
-            fb = fem.FacetBasis(m, e, facets=ob, side=side)
-            assert np.array_equal(fb.tind, g[k + "_tind"])
-            assert np.array_equal(fb.normals.numpy(), g[k + "_normals"])
-            assert np.array_equal(fb.dx, g[k + "_dx"])
-            A = flow.assemble(fb)
-            assert np.array_equal(A.indptr, g[k + "_indptr"])
-            assert np.array_equal(A.indices, g[k + "_indices"])
-            ref = g[k + "_data"]
-            np.testing.assert_allclose(A.data, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
-            np.testing.assert_allclose(divthm.assemble(fb), float(g[k + "_divthm"]), rtol=1e-12)
-
-
-@pytest.mark.gpu
 def test_gpu_facet_vector():
     import skfem_b200 as fem
     from skfem_b200.helpers import dot, grad

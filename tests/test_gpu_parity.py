@@ -50,8 +50,7 @@ def test_against_reference_golden(name):
 
 
 @pytest.mark.parametrize("sumfact", [True, False])
-@pytest.mark.parametrize("name", ["hex2_tensor2", "hex2_morphed2", "hex2_morphed4",
-                                  "hex2_boxes3"])
+@pytest.mark.parametrize("name", ["hex2_tensor2", "hex2_morphed2", "hex2_morphed4"])
 def test_hex2_value_parity(name, sumfact):
     """Hex2 at the default rule: the sum-factorised kernel (csrc/skb_hex_sf.cu) and the FP64
     tensor-core Gram kernel behind it (csrc/skb_hex_mma.cu, with the reference's own tables)
